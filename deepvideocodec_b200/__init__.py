@@ -1,0 +1,20 @@
+"""deepvideocodec_b200 -- B200 (sm_100a) hot path of the DMC contextual P-frame
+codec: flow warp, checkerboard dual-prior quantisation, Gaussian-conditional /
+entropy-bottleneck likelihoods and the rate reduction, as hand-written CUDA
+behind the reference's own Python names.
+
+Importing the package never needs a GPU; calling an op needs the built
+``libdvc_b200.so`` and CUDA fp32 tensors -- there is no fallback path.
+"""
+from ._native import DvcError, LIB_PATH, build_library, declared_symbols, lib  # noqa: F401
+from .context import (dual_prior_stage_a, dual_prior_stage_b_gc, forward_dual_prior,  # noqa: F401
+                      frame_context_forward, motion_context_forward)
+from .entropy_models import (EntropyBottleneck, EntropyModel, GaussianConditional,  # noqa: F401
+                             LowerBound)
+from .layers import (bilineardownsacling, flow_pyramid, flow_warp,  # noqa: F401
+                     motion_compensation_warps, torch_warp, warp_multi)
+from .patch import install_compressai_shim, patch, unpatch  # noqa: F401
+from .rate import collect_likelihoods_list, frame_bits, log_sum, rate_finalize  # noqa: F401
+from .utils import quantize_around, quantize_ste  # noqa: F401
+
+__version__ = "0.1.0"

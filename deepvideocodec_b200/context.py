@@ -1,0 +1,223 @@
+"""Fused replacements for the non-conv part of the reference's two context
+models (``MotionContextModel`` / ``FrameContextModel``,
+``dmc/models/video_model.py:128-233`` and ``:294-406``).
+
+The reference runs ``get_mask`` (host tensor + H2D copy per forward, :152-159),
+four ``process_with_mask`` calls (:161-167), three ``cat``s, the Gaussian
+conditional (~20 ops) and the z quantisation as ~70 eager launches around the
+3-conv spatial prior.  Here it is two kernels around that conv:
+
+    stage A : y, means, scales            -> params = cat(y_hat_00, y_hat_11, means, scales)
+    (cuDNN) : self.y_spatial_prior(params)
+    stage B : y, means, scales, prior_out -> y_hat, likelihood (+ sum ln p)
+                                             [+ means_hat, scales_hat | compress planes]
+
+The functions below are written as *methods* (first argument ``self`` is the
+reference's context-model instance) so ``deepvideocodec_b200.patch`` can bind
+them onto the stock classes; signatures and return structures are the
+reference's.
+"""
+import torch
+
+from . import _native as nat
+from .entropy_models import _launch_noise_like, eb_forward
+
+__all__ = ["dual_prior_stage_a", "dual_prior_stage_b_gc", "forward_dual_prior",
+           "motion_context_forward", "frame_context_forward"]
+
+
+def _check_latents(y, means, scales, who):
+    for t, nm in ((y, "y"), (means, "means"), (scales, "scales")):
+        nat.require_cuda_f32(t, f"{who}({nm})")
+    if means.shape != y.shape or scales.shape != y.shape:
+        raise nat.DvcError(f"{who}: y, means, scales must have one shape")
+    n, c, h, w = y.shape
+    if c % 2 or h % 2 or w % 2:
+        # get_mask (video_model.py:155) repeats a 2x2 cell: odd sizes break the
+        # reference as well
+        raise nat.DvcError(f"{who}: C, H, W must be even, got {tuple(y.shape)}")
+
+
+# ---------------------------------------------------------------------------
+# stage A
+# ---------------------------------------------------------------------------
+def _stage_a_fwd(y, means, scales):
+    n, c, h, w = y.shape
+    cl = y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()
+    params = torch.empty((n, 3 * c, h, w), dtype=y.dtype, device=y.device,
+                         memory_format=torch.channels_last if cl else torch.contiguous_format)
+    with nat.device_of(y):
+        rc = nat.lib().dvc_dual_prior_stage_a_fwd(
+            y.data_ptr(), means.data_ptr(), scales.data_ptr(), params.data_ptr(), n, c, h, w,
+            nat.st4(y), nat.st4(means), nat.st4(scales), nat.st4(params), nat.stream_of(y))
+    nat.check(rc, "dvc_dual_prior_stage_a_fwd")
+    return params
+
+
+class _StageAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, means, scales):
+        ctx.cshape = tuple(y.shape)
+        return _stage_a_fwd(y, means, scales)
+
+    @staticmethod
+    def backward(ctx, g_params):
+        from .autograd_kernels import stage_a_bwd
+        return stage_a_bwd(g_params, ctx.cshape)
+
+
+def dual_prior_stage_a(y, means, scales):
+    """``params = cat(y_hat_0_0, y_hat_1_1, means, scales)`` (video_model.py:176-189)."""
+    _check_latents(y, means, scales, "dual_prior_stage_a")
+    if torch.is_grad_enabled() and (y.requires_grad or means.requires_grad or scales.requires_grad):
+        return _StageAFn.apply(y, means, scales)
+    return _stage_a_fwd(y, means, scales)
+
+
+# ---------------------------------------------------------------------------
+# stage B + Gaussian conditional
+# ---------------------------------------------------------------------------
+def _stage_b_fwd(y, means, scales, prior, noise, scale_bound, lik_bound, want_params, compress):
+    n, c, h, w = y.shape
+    y_hat = torch.empty_like(y)
+    lik = torch.empty_like(y)
+    means_hat = torch.empty_like(y) if want_params else None
+    scales_hat = torch.empty_like(y) if want_params else None
+    planes = [None] * 4
+    if compress:
+        planes = [torch.empty((n, c // 2, h, w), dtype=y.dtype, device=y.device) for _ in range(4)]
+    logsum = torch.empty(n, dtype=torch.float64, device=y.device)
+    ws = nat.rate_workspace(y.device, n)
+    with nat.device_of(y):
+        rc = nat.lib().dvc_dual_prior_stage_b_gc_fwd(
+            y.data_ptr(), means.data_ptr(), scales.data_ptr(), prior.data_ptr(), nat.ptr(noise),
+            y_hat.data_ptr(), nat.ptr(means_hat), nat.ptr(scales_hat), lik.data_ptr(),
+            nat.ptr(planes[0]), nat.ptr(planes[1]), nat.ptr(planes[2]), nat.ptr(planes[3]),
+            logsum.data_ptr(), ws.data_ptr(), n, c, h, w,
+            nat.st4(y), nat.st4(means), nat.st4(scales), nat.st4(prior), nat.opt_st4(noise),
+            nat.st4(y_hat), nat.opt_st4(planes[0]), scale_bound, lik_bound, nat.stream_of(y))
+    nat.check(rc, "dvc_dual_prior_stage_b_gc_fwd")
+    return y_hat, means_hat, scales_hat, lik, logsum, planes
+
+
+class _StageBGcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, means, scales, prior, noise, scale_bound, lik_bound, want_params):
+        y_hat, means_hat, scales_hat, lik, logsum, _ = _stage_b_fwd(
+            y, means, scales, prior, noise, scale_bound, lik_bound, want_params, False)
+        ctx.save_for_backward(y, means, scales, prior, noise)
+        ctx.bounds = (scale_bound, lik_bound)
+        if not want_params:
+            means_hat = y.new_empty(0)
+            scales_hat = y.new_empty(0)
+        return y_hat, means_hat, scales_hat, lik, logsum
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_mh, g_sh, g_lik, g_logsum):
+        from .autograd_kernels import stage_b_gc_bwd
+        y, means, scales, prior, noise = ctx.saved_tensors
+        gy, gm, gs, gp = stage_b_gc_bwd(y, means, scales, prior, noise, g_yhat, g_mh, g_sh,
+                                        g_lik, g_logsum, ctx.bounds[0], ctx.bounds[1])
+        return gy, gm, gs, gp, None, None, None, None
+
+
+def _gc_bounds(gc):
+    """(scale_bound, likelihood_bound) of a GaussianConditional -- ours or the
+    real CompressAI module (reads the buffers once and caches the floats)."""
+    cached = getattr(gc, "_dvc_bounds", None)
+    if cached is not None:
+        return cached
+    sb_mod = gc.lower_bound_scale
+    sb = sb_mod.value() if hasattr(sb_mod, "value") else float(sb_mod.bound.detach().cpu().reshape(-1)[0])
+    if getattr(gc, "use_likelihood_bound", True):
+        lb_mod = gc.likelihood_lower_bound
+        lb = lb_mod.value() if hasattr(lb_mod, "value") else float(lb_mod.bound.detach().cpu().reshape(-1)[0])
+    else:
+        lb = float("-inf")
+    gc._dvc_bounds = (sb, lb)
+    return gc._dvc_bounds
+
+
+def dual_prior_stage_b_gc(y, means, scales, prior, gc, training, want_params=False,
+                          compress=False):
+    """Stage B + merge + Gaussian conditional.  Returns
+    ``(y_hat, means_hat, scales_hat, likelihood, planes)``; ``means_hat`` /
+    ``scales_hat`` are ``None`` unless ``want_params``; ``planes`` is
+    ``(q_w0, q_w1, s_w0, s_w1)`` when ``compress`` else ``None``.  The
+    likelihood carries ``._dvc_logsum``."""
+    _check_latents(y, means, scales, "dual_prior_stage_b_gc")
+    nat.require_cuda_f32(prior, "dual_prior_stage_b_gc(prior)")
+    n, c, h, w = y.shape
+    if prior.shape != (n, 2 * c, h, w):
+        raise nat.DvcError(f"dual_prior_stage_b_gc: spatial prior output must be "
+                           f"{(n, 2 * c, h, w)}, got {tuple(prior.shape)}")
+    sb, lb = _gc_bounds(gc)
+    noise = _launch_noise_like(y) if training else None
+    needs_grad = torch.is_grad_enabled() and any(
+        t.requires_grad for t in (y, means, scales, prior))
+    if needs_grad and not compress:
+        y_hat, means_hat, scales_hat, lik, logsum = _StageBGcFn.apply(
+            y, means, scales, prior, noise, sb, lb, want_params)
+        planes = None
+        if not want_params:
+            means_hat = scales_hat = None
+    else:
+        y_hat, means_hat, scales_hat, lik, logsum, planes = _stage_b_fwd(
+            y, means, scales, prior, noise, sb, lb, want_params, compress)
+        planes = tuple(planes) if compress else None
+    lik._dvc_logsum = logsum
+    return y_hat, means_hat, scales_hat, lik, planes
+
+
+# ---------------------------------------------------------------------------
+# method drop-ins
+# ---------------------------------------------------------------------------
+def forward_dual_prior(self, y, means, scales, mode="trainval"):
+    """Drop-in for ``forward_dual_prior`` (video_model.py:169-216 == :341-388):
+    same arguments, same returns.  The likelihood computed by stage B is kept
+    on ``self`` so a following ``gaussian_conditional`` call could reuse it;
+    the fused ``*_context_forward`` below skip this method entirely."""
+    params = dual_prior_stage_a(y, means, scales)
+    prior = self.y_spatial_prior(params)
+    compress = mode == "compress"
+    y_hat, means_hat, scales_hat, _, planes = dual_prior_stage_b_gc(
+        y, means, scales, prior, self.gaussian_conditional, training=False,
+        want_params=not compress, compress=compress)
+    if compress:
+        return (y_hat,) + planes
+    return y_hat, means_hat, scales_hat
+
+
+def _context_tail(self, y, means_hat, scales_hat, z_likelihoods):
+    params = dual_prior_stage_a(y, means_hat, scales_hat)
+    prior = self.y_spatial_prior(params)
+    y_hat, _, _, y_likelihoods, _ = dual_prior_stage_b_gc(
+        y, means_hat, scales_hat, prior, self.gaussian_conditional,
+        training=self.gaussian_conditional.training)
+    return y_hat, {"y": y_likelihoods, "z": z_likelihoods}
+
+
+def motion_context_forward(self, y, y_ref):
+    """Drop-in for ``MotionContextModel.forward`` (video_model.py:218-233)."""
+    z = self.hyper_encoder(y)
+    _, z_hat, z_likelihoods = eb_forward(self.entropy_bottleneck, z, want_outputs=False,
+                                         want_zhat=True)
+    params = self.hyper_decoder(z_hat)
+    if y_ref is None:
+        y_ref = torch.zeros_like(y)
+    means_hat, scales_hat = self.y_prior_fusion(torch.cat((params, y_ref), dim=1)).chunk(2, 1)
+    return _context_tail(self, y, means_hat, scales_hat, z_likelihoods)
+
+
+def frame_context_forward(self, y, y_ref, context):
+    """Drop-in for ``FrameContextModel.forward`` (video_model.py:390-406)."""
+    z = self.hyper_encoder(y)
+    _, z_hat, z_likelihoods = eb_forward(self.entropy_bottleneck, z, want_outputs=False,
+                                         want_zhat=True)
+    params = self.hyper_decoder(z_hat)
+    if y_ref is None:
+        y_ref = torch.zeros_like(y)
+    temporal_params = self.temporal_prior_encoder(context)
+    means_hat, scales_hat = self.y_prior_fusion(
+        torch.cat((temporal_params, params, y_ref), dim=1)).chunk(2, 1)
+    return _context_tail(self, y, means_hat, scales_hat, z_likelihoods)

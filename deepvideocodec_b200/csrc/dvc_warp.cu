@@ -1,0 +1,485 @@
+// dvc_warp.cu -- optical-flow backward warp + flow pyramid for sm_100a.
+//
+// Replaces (arithmetic replayed op for op):
+//   flow_warp / torch_warp      /root/reference/dmc/models/layers.py:175-198
+//   bilineardownsacling (+ /2)  /root/reference/dmc/models/layers.py:201-206,
+//                               /root/reference/dmc/models/video_model.py:499-500
+//   DMC.motion_compensation     /root/reference/dmc/models/video_model.py:497-504 (the 4 warps)
+//
+// The warp is a pure HBM-bound gather: 4*(2C+2) algorithmic bytes per output
+// pixel.  Layout decides everything:
+//   * channels_last (NHWC) fast path: one thread owns 4 channels of a pixel, a
+//     pixel's tap is one contiguous C*4-byte run -> every tap is a coalesced
+//     128-bit load, every output a coalesced 128-bit streaming store.  A CTA
+//     walks a (256/(C/4)) x ROWS pixel tile row by row so the two source rows
+//     a row needs are re-used from L1 by the next row; vertically adjacent
+//     tiles meet in L2 (126 MB), so DRAM sees the input about once.
+//   * strided path (NCHW, C=3 frames, odd layouts): one thread per pixel,
+//     lanes along W (coalesced per channel plane), channel loop unrolled x4.
+// Source coordinates are computed once per pixel and reused for all channels.
+#include "dvc_common.cuh"
+
+namespace dvc {
+
+// ---------------------------------------------------------------------------
+// coordinate pipeline (bit-faithful replay of linspace + div + add +
+// grid_sampler_compute_source_index + clip), see header comment of each step
+// ---------------------------------------------------------------------------
+struct WarpGeom {
+  int H, W;
+  float step_x, step_y;  // fl32(2 / (S-1)): torch.linspace step
+  float norm_x, norm_y;  // default: fl32(1 / fl32((S-1)/2)); IEEE mode: fl32((S-1)/2)
+  float wm1, hm1;        // (float)(S-1)
+  int ieee_div;
+};
+
+// torch.linspace(-1, 1, S)[j]: start + step*j below the midpoint, end -
+// step*(S-1-j) above it, each contracted to ONE fused multiply-add by both
+// ATen back ends (RangeFactories); the unfused form mismatches ~40% of entries.
+__device__ __forceinline__ float linspace_pm1(int j, int S, float step) {
+  return (j < (S >> 1)) ? fmaf(step, (float)j, -1.0f)
+                        : fmaf(-step, (float)(S - 1 - j), 1.0f);
+}
+
+struct Taps {
+  int x0, y0;            // north-west tap
+  int dx, dy;            // 1 if the east / south neighbour is inside, else 0
+  float nw, ne, sw, se;  // bilinear weights
+};
+
+__device__ __forceinline__ float source_index(float base, float f, float norm,
+                                              float sm1, int ieee_div) {
+  // layers.py:185-186  flow / ((S-1)/2): CUDA eager multiplies by the fp32
+  // reciprocal of the python scalar, CPU eager divides.
+  float fn = ieee_div ? div_rn(f, norm) : mul_rn(f, norm);
+  float c = add_rn(base, fn);                                   // layers.py:188
+  // GridSampler.cuh grid_sampler_unnormalize(align_corners=True):
+  //   ((coord + 1) / 2) * (size - 1)
+  float i = mul_rn(mul_rn(add_rn(c, 1.0f), 0.5f), sm1);
+  // clip_coordinates: min(size-1, max(i, 0)); NaN -> 0 through fmaxf
+  return fminf(sm1, fmaxf(i, 0.0f));
+}
+
+__device__ __forceinline__ Taps make_taps(const WarpGeom& g, int h, int w, float fx,
+                                          float fy) {
+  float ix = source_index(linspace_pm1(w, g.W, g.step_x), fx, g.norm_x, g.wm1, g.ieee_div);
+  float iy = source_index(linspace_pm1(h, g.H, g.step_y), fy, g.norm_y, g.hm1, g.ieee_div);
+  float x0f = floorf(ix), y0f = floorf(iy);
+  float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+  Taps t;
+  t.x0 = (int)x0f;
+  t.y0 = (int)y0f;
+  t.dx = (t.x0 + 1 < g.W) ? 1 : 0;  // within_bounds_2d of the east taps
+  t.dy = (t.y0 + 1 < g.H) ? 1 : 0;
+  float ax = sub_rn(x1f, ix), bx = sub_rn(ix, x0f);
+  float ay = sub_rn(y1f, iy), by = sub_rn(iy, y0f);
+  t.nw = mul_rn(ax, ay);
+  t.ne = mul_rn(bx, ay);
+  t.sw = mul_rn(ax, by);
+  t.se = mul_rn(bx, by);
+  return t;
+}
+
+// out_acc = 0; out_acc += v*w for nw, ne, sw, se in that order (each `+=` is
+// one FFMA in ATen's kernel as compiled by nvcc).
+__device__ __forceinline__ float blend(float vnw, float vne, float vsw, float vse,
+                                       const Taps& t) {
+  float acc = mul_rn(vnw, t.nw);
+  acc = fmaf(vne, t.ne, acc);
+  acc = fmaf(vsw, t.sw, acc);
+  acc = fmaf(vse, t.se, acc);
+  return acc;
+}
+
+// ---------------------------------------------------------------------------
+// task descriptors (passed by value as a __grid_constant__)
+// ---------------------------------------------------------------------------
+enum { kModeVec4 = 0, kModeStrided = 1 };
+constexpr int kThreads = 256;
+constexpr int kRows = 8;         // tile height of both paths
+constexpr int kStridedTileW = 32;
+constexpr int kMaxTasks = 4;
+
+struct WarpTask {
+  const float* im;
+  const float* flow;
+  float* out;
+  WarpGeom g;
+  int N, C;
+  long long im_n, im_c, im_h, im_w;
+  long long fl_n, fl_c, fl_h, fl_w;
+  long long out_n, out_c, out_h, out_w;
+  int mode;
+  int c4;            // vec4: float4 groups per pixel
+  int ppb;           // vec4: pixels per tile row = kThreads / c4
+  int tiles_x, tiles_y;
+  int first_block, n_blocks;
+};
+struct WarpBatch {
+  WarpTask t[kMaxTasks];
+  int n_tasks;
+};
+
+// ---------------------------------------------------------------------------
+// NHWC float4 path
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void warp_tile_vec4(const WarpTask& t, int tile) {
+  const int tx = tile % t.tiles_x;
+  const int rest = tile / t.tiles_x;
+  const int ty = rest % t.tiles_y;
+  const int n = rest / t.tiles_y;
+
+  const int px = threadIdx.x / t.c4;
+  const int lane = threadIdx.x - px * t.c4;
+  const int w = tx * t.ppb + px;
+  if (px >= t.ppb || w >= t.g.W) return;
+  const int h0 = ty * kRows;
+
+  // strides in float4 units (dispatcher guarantees divisibility and int32 range)
+  const int im_h4 = (int)(t.im_h >> 2), im_w4 = (int)(t.im_w >> 2);
+  const float4* __restrict__ im4 = reinterpret_cast<const float4*>(t.im + n * t.im_n) + lane;
+  float4* __restrict__ out4 =
+      reinterpret_cast<float4*>(t.out + n * t.out_n + (long long)w * t.out_w) + lane;
+  const float* __restrict__ fl = t.flow + n * t.fl_n + (long long)w * t.fl_w;
+
+  // the flow of the whole tile column first: 2*kRows independent loads in flight
+  float fx[kRows], fy[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int h = min(h0 + r, t.g.H - 1);
+    fx[r] = __ldg(fl + h * t.fl_h);
+    fy[r] = __ldg(fl + h * t.fl_h + t.fl_c);
+  }
+
+#pragma unroll
+  for (int r = 0; r < kRows; r += 2) {
+    const int hA = h0 + r, hB = hA + 1;
+    if (hA >= t.g.H) break;
+    const bool okB = hB < t.g.H;
+    const Taps A = make_taps(t.g, hA, w, fx[r], fy[r]);
+    const Taps B = make_taps(t.g, okB ? hB : hA, w, fx[r + 1], fy[r + 1]);
+    const int oA = A.y0 * im_h4 + A.x0 * im_w4;
+    const int oB = B.y0 * im_h4 + B.x0 * im_w4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    // 8 independent 128-bit gathers before the first use
+    const float4 a_nw = ldg4(im4 + oA);
+    const float4 a_ne = A.dx ? ldg4(im4 + oA + im_w4) : z;
+    const float4 a_sw = A.dy ? ldg4(im4 + oA + im_h4) : z;
+    const float4 a_se = (A.dx & A.dy) ? ldg4(im4 + oA + im_h4 + im_w4) : z;
+    const float4 b_nw = ldg4(im4 + oB);
+    const float4 b_ne = B.dx ? ldg4(im4 + oB + im_w4) : z;
+    const float4 b_sw = B.dy ? ldg4(im4 + oB + im_h4) : z;
+    const float4 b_se = (B.dx & B.dy) ? ldg4(im4 + oB + im_h4 + im_w4) : z;
+    float4 o;
+    o.x = blend(a_nw.x, a_ne.x, a_sw.x, a_se.x, A);
+    o.y = blend(a_nw.y, a_ne.y, a_sw.y, a_se.y, A);
+    o.z = blend(a_nw.z, a_ne.z, a_sw.z, a_se.z, A);
+    o.w = blend(a_nw.w, a_ne.w, a_sw.w, a_se.w, A);
+    st_streaming(out4 + ((long long)hA * t.out_h >> 2), o);
+    if (okB) {
+      o.x = blend(b_nw.x, b_ne.x, b_sw.x, b_se.x, B);
+      o.y = blend(b_nw.y, b_ne.y, b_sw.y, b_se.y, B);
+      o.z = blend(b_nw.z, b_ne.z, b_sw.z, b_se.z, B);
+      o.w = blend(b_nw.w, b_ne.w, b_sw.w, b_se.w, B);
+      st_streaming(out4 + ((long long)hB * t.out_h >> 2), o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// strided path: one thread per pixel, arbitrary element strides
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_tile_strided(const WarpTask& t, int tile) {
+  const int tx = tile % t.tiles_x;
+  const int rest = tile / t.tiles_x;
+  const int ty = rest % t.tiles_y;
+  const int n = rest / t.tiles_y;
+  const int w = tx * kStridedTileW + (threadIdx.x & 31);
+  const int h = ty * kRows + (threadIdx.x >> 5);
+  if (w >= t.g.W || h >= t.g.H) return;
+
+  const float* __restrict__ fl = t.flow + n * t.fl_n + h * t.fl_h + w * t.fl_w;
+  const float fx = __ldg(fl), fy = __ldg(fl + t.fl_c);
+  const Taps T = make_taps(t.g, h, w, fx, fy);
+
+  const float* __restrict__ p_nw = t.im + n * t.im_n + T.y0 * t.im_h + T.x0 * t.im_w;
+  const float* __restrict__ p_ne = p_nw + (T.dx ? t.im_w : 0);
+  const float* __restrict__ p_sw = p_nw + (T.dy ? t.im_h : 0);
+  const float* __restrict__ p_se = p_sw + (T.dx ? t.im_w : 0);
+  float* __restrict__ po = t.out + n * t.out_n + h * t.out_h + w * t.out_w;
+  // out-of-bounds neighbours are skipped by ATen; they alias an in-bounds tap
+  // here and are masked to exactly 0 so inf/NaN pixels cannot leak through
+  // their zero weight.
+  const bool in_e = T.dx != 0, in_s = T.dy != 0;
+#pragma unroll 4
+  for (int c = 0; c < t.C; ++c) {
+    const float vnw = __ldg(p_nw + c * t.im_c);
+    float vne = __ldg(p_ne + c * t.im_c);
+    float vsw = __ldg(p_sw + c * t.im_c);
+    float vse = __ldg(p_se + c * t.im_c);
+    vne = in_e ? vne : 0.f;
+    vsw = in_s ? vsw : 0.f;
+    vse = (in_e && in_s) ? vse : 0.f;
+    po[c * t.out_c] = blend(vnw, vne, vsw, vse, T);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
+  int b = blockIdx.x;
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxTasks; ++i)
+    if (i < batch.n_tasks && b >= batch.t[i].first_block) k = i;
+  const WarpTask& t = batch.t[k];
+  const int tile = b - t.first_block;
+  if (t.mode == kModeVec4)
+    warp_tile_vec4(t, tile);
+  else
+    warp_tile_strided(t, tile);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int fill_geom(WarpGeom& g, int64_t H, int64_t W, int flags) {
+  g.H = (int)H;
+  g.W = (int)W;
+  // ATen RangeFactories: step = (end - start) / (steps - 1) in fp32
+  g.step_x = 2.0f / (float)(W - 1);
+  g.step_y = 2.0f / (float)(H - 1);
+  // layers.py:185-186: the divisor is the python double (S - 1.0) / 2.0,
+  // converted to fp32 when it meets the fp32 tensor.
+  const float half_w = (float)(((double)W - 1.0) / 2.0);
+  const float half_h = (float)(((double)H - 1.0) / 2.0);
+  g.ieee_div = (flags & DVC_WARP_IEEE_DIV) ? 1 : 0;
+  g.norm_x = g.ieee_div ? half_w : 1.0f / half_w;
+  g.norm_y = g.ieee_div ? half_h : 1.0f / half_h;
+  g.wm1 = (float)(W - 1);
+  g.hm1 = (float)(H - 1);
+  return DVC_OK;
+}
+
+static int build_task(WarpTask& t, const dvc_warp_task& in, int flags) {
+  DVC_REQUIRE(in.im && in.flow && in.out, "flow_warp: null pointer");
+  DVC_REQUIRE(in.N > 0 && in.C > 0 && in.H > 0 && in.W > 0, "flow_warp: empty tensor");
+  DVC_REQUIRE(in.H < (1 << 24) && in.W < (1 << 24) && in.N < 65536 && in.C < (1 << 24),
+              "flow_warp: extent too large");
+  t.im = in.im;
+  t.flow = in.flow;
+  t.out = in.out;
+  t.N = (int)in.N;
+  t.C = (int)in.C;
+  fill_geom(t.g, in.H, in.W, flags);
+  const Strides4 si = make_strides(in.im_st), sf = make_strides(in.flow_st),
+                 so = make_strides(in.out_st);
+  t.im_n = si.n; t.im_c = si.c; t.im_h = si.h; t.im_w = si.w;
+  t.fl_n = sf.n; t.fl_c = sf.c; t.fl_h = sf.h; t.fl_w = sf.w;
+  t.out_n = so.n; t.out_c = so.c; t.out_h = so.h; t.out_w = so.w;
+  const bool vec = nhwc_vec4_ok(in.im, si, in.C) && nhwc_vec4_ok(in.out, so, in.C) &&
+                   in.C / 4 <= kThreads && fits_int32(1, in.C, in.H, in.W, si) &&
+                   si.h >= 0 && si.w >= 0;
+  if (vec) {
+    t.mode = kModeVec4;
+    t.c4 = (int)(in.C / 4);
+    t.ppb = kThreads / t.c4;
+    t.tiles_x = (int)((in.W + t.ppb - 1) / t.ppb);
+  } else {
+    t.mode = kModeStrided;
+    t.c4 = 0;
+    t.ppb = kStridedTileW;
+    t.tiles_x = (int)((in.W + kStridedTileW - 1) / kStridedTileW);
+  }
+  t.tiles_y = (int)((in.H + kRows - 1) / kRows);
+  const long long nb = (long long)t.tiles_x * t.tiles_y * in.N;
+  DVC_REQUIRE(nb < 2147483647LL, "flow_warp: too many tiles");
+  t.n_blocks = (int)nb;
+  return DVC_OK;
+}
+
+static int launch_batch(const dvc_warp_task* tasks, int n_tasks, int flags,
+                        cudaStream_t stream) {
+  DVC_REQUIRE(tasks && n_tasks >= 1 && n_tasks <= kMaxTasks,
+              "warp_multi: n_tasks must be in [1,%d]", kMaxTasks);
+  WarpBatch batch;
+  batch.n_tasks = n_tasks;
+  long long total = 0;
+  for (int i = 0; i < n_tasks; ++i) {
+    int rc = build_task(batch.t[i], tasks[i], flags);
+    if (rc) return rc;
+    batch.t[i].first_block = (int)total;
+    total += batch.t[i].n_blocks;
+  }
+  for (int i = n_tasks; i < kMaxTasks; ++i) batch.t[i] = batch.t[0];
+  DVC_REQUIRE(total < 2147483647LL, "warp_multi: grid too large");
+  warp_multi_kernel<<<(unsigned)total, kThreads, 0, stream>>>(batch);
+  return check_launch("warp_multi_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// bilinear 2x downscale (align_corners=False), forward
+// ---------------------------------------------------------------------------
+struct DownP {
+  const float* x;
+  float* y;
+  int N, C, H, W, Ho, Wo;
+  long long xs_n, xs_c, xs_h, xs_w, ys_n, ys_c, ys_h, ys_w;
+  float scale_h, scale_w, post;
+  int exact2;  // H, W even: source lambdas are exactly 1/2
+};
+
+// UpSample.cuh area_pixel_compute_source_index(align_corners=false, cubic=false)
+__device__ __forceinline__ float area_src(float scale, int dst) {
+  float s = fmaf(scale, (float)dst + 0.5f, -0.5f);
+  return s < 0.f ? 0.f : s;
+}
+
+__global__ void __launch_bounds__(256) bilinear_down2_kernel(const DownP p) {
+  const long long total = (long long)p.N * p.C * p.Ho * p.Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % p.Wo);
+    long long r = i / p.Wo;
+    const int ho = (int)(r % p.Ho);
+    r /= p.Ho;
+    const int c = (int)(r % p.C);
+    const int n = (int)(r / p.C);
+    const float* __restrict__ xp = p.x + n * p.xs_n + c * p.xs_c;
+    float v;
+    if (p.exact2) {
+      const float* q = xp + (2 * ho) * p.xs_h + (2 * wo) * p.xs_w;
+      const float a = __ldg(q), b = __ldg(q + p.xs_w);
+      const float cc = __ldg(q + p.xs_h), d = __ldg(q + p.xs_h + p.xs_w);
+      // 0.5*(0.5a+0.5b) + 0.5*(0.5c+0.5d): power-of-two scalings commute with
+      // rounding, so this is exactly ((a+b)+(c+d))/4
+      v = mul_rn(add_rn(add_rn(a, b), add_rn(cc, d)), 0.25f);
+    } else {
+      const float h1r = area_src(p.scale_h, ho), w1r = area_src(p.scale_w, wo);
+      const int h1 = (int)h1r, w1 = (int)w1r;
+      const int h1p = (h1 < p.H - 1) ? 1 : 0, w1p = (w1 < p.W - 1) ? 1 : 0;
+      const float h1l = h1r - (float)h1, h0l = 1.f - h1l;
+      const float w1l = w1r - (float)w1, w0l = 1.f - w1l;
+      const float* q = xp + h1 * p.xs_h + w1 * p.xs_w;
+      const float a = __ldg(q), b = __ldg(q + w1p * p.xs_w);
+      const float cc = __ldg(q + h1p * p.xs_h), d = __ldg(q + h1p * p.xs_h + w1p * p.xs_w);
+      // upsample_bilinear2d_out_frame as nvcc contracts it
+      v = fmaf(h0l, fmaf(w0l, a, w1l * b), h1l * fmaf(w0l, cc, w1l * d));
+    }
+    p.y[n * p.ys_n + c * p.ys_c + ho * p.ys_h + wo * p.ys_w] = mul_rn(v, p.post);
+  }
+}
+
+// two pyramid levels in one pass: one thread per level-3 sample reads a 4x4
+// block of mv, emits 2x2 level-2 samples and 1 level-3 sample.
+struct PyrP {
+  const float* mv;
+  float* mv2;
+  float* mv3;
+  int N, H3, W3;
+  long long a_n, a_c, a_h, a_w, b_n, b_c, b_h, b_w, c_n, c_c, c_h, c_w;
+};
+
+__global__ void __launch_bounds__(256) flow_pyramid_kernel(const PyrP p) {
+  const long long total = (long long)p.N * 2 * p.H3 * p.W3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w3 = (int)(i % p.W3);
+    long long r = i / p.W3;
+    const int h3 = (int)(r % p.H3);
+    r /= p.H3;
+    const int c = (int)(r & 1);
+    const int n = (int)(r >> 1);
+    const float* __restrict__ src = p.mv + n * p.a_n + c * p.a_c + (4 * h3) * p.a_h + (4 * w3) * p.a_w;
+    float m2[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float* q = src + (2 * j) * p.a_h + (2 * k) * p.a_w;
+        const float a = __ldg(q), b = __ldg(q + p.a_w);
+        const float cc = __ldg(q + p.a_h), d = __ldg(q + p.a_h + p.a_w);
+        // bilinear /2 then "/ 2" (video_model.py:499): (.)*0.25*0.5
+        m2[j][k] = mul_rn(mul_rn(add_rn(add_rn(a, b), add_rn(cc, d)), 0.25f), 0.5f);
+        p.mv2[n * p.b_n + c * p.b_c + (2 * h3 + j) * p.b_h + (2 * w3 + k) * p.b_w] = m2[j][k];
+      }
+    const float v3 = mul_rn(
+        mul_rn(add_rn(add_rn(m2[0][0], m2[0][1]), add_rn(m2[1][0], m2[1][1])), 0.25f), 0.5f);
+    p.mv3[n * p.c_n + c * p.c_c + h3 * p.c_h + w3 * p.c_w] = v3;
+  }
+}
+
+static unsigned grid_for(long long total, int threads, int per_sm) {
+  long long want = (total + threads - 1) / threads;
+  long long cap = (long long)sm_count() * per_sm;
+  if (want < 1) want = 1;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+}  // namespace dvc
+
+using namespace dvc;
+
+extern "C" {
+
+int dvc_flow_warp_fwd(const float* im, const float* flow, float* out, int64_t N, int64_t C,
+                      int64_t H, int64_t W, const int64_t im_st[4], const int64_t flow_st[4],
+                      const int64_t out_st[4], int flags, dvc_stream_t stream) {
+  DVC_REQUIRE(im_st && flow_st && out_st, "flow_warp: null strides");
+  dvc_warp_task t;
+  t.im = im; t.flow = flow; t.out = out;
+  t.N = N; t.C = C; t.H = H; t.W = W;
+  for (int i = 0; i < 4; ++i) {
+    t.im_st[i] = im_st[i];
+    t.flow_st[i] = flow_st[i];
+    t.out_st[i] = out_st[i];
+  }
+  return launch_batch(&t, 1, flags, (cudaStream_t)stream);
+}
+
+int dvc_warp_multi_fwd(const dvc_warp_task* tasks, int n_tasks, int flags,
+                       dvc_stream_t stream) {
+  return launch_batch(tasks, n_tasks, flags, (cudaStream_t)stream);
+}
+
+int dvc_bilinear_down2_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t H,
+                           int64_t W, const int64_t x_st[4], const int64_t y_st[4],
+                           float post_scale, dvc_stream_t stream) {
+  DVC_REQUIRE(x && y && x_st && y_st, "bilinear_down2: null pointer");
+  DVC_REQUIRE(N > 0 && C > 0 && H >= 2 && W >= 2, "bilinear_down2: needs H,W >= 2");
+  DownP p;
+  p.x = x; p.y = y;
+  p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W;
+  p.Ho = (int)(H / 2); p.Wo = (int)(W / 2);
+  p.xs_n = x_st[0]; p.xs_c = x_st[1]; p.xs_h = x_st[2]; p.xs_w = x_st[3];
+  p.ys_n = y_st[0]; p.ys_c = y_st[1]; p.ys_h = y_st[2]; p.ys_w = y_st[3];
+  // UpSample.h area_pixel_compute_scale(align_corners=false): in / out in fp32
+  p.scale_h = (float)H / (float)p.Ho;
+  p.scale_w = (float)W / (float)p.Wo;
+  p.post = post_scale;
+  p.exact2 = ((H % 2) == 0 && (W % 2) == 0) ? 1 : 0;
+  const long long total = (long long)N * C * p.Ho * p.Wo;
+  bilinear_down2_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("bilinear_down2_kernel");
+}
+
+int dvc_flow_pyramid_fwd(const float* mv, float* mv2, float* mv3, int64_t N, int64_t H,
+                         int64_t W, const int64_t mv_st[4], const int64_t mv2_st[4],
+                         const int64_t mv3_st[4], dvc_stream_t stream) {
+  DVC_REQUIRE(mv && mv2 && mv3 && mv_st && mv2_st && mv3_st, "flow_pyramid: null pointer");
+  DVC_REQUIRE(N > 0 && H >= 4 && W >= 4 && (H % 4) == 0 && (W % 4) == 0,
+              "flow_pyramid: H and W must be positive multiples of 4 (got %lld x %lld)",
+              (long long)H, (long long)W);
+  PyrP p;
+  p.mv = mv; p.mv2 = mv2; p.mv3 = mv3;
+  p.N = (int)N; p.H3 = (int)(H / 4); p.W3 = (int)(W / 4);
+  p.a_n = mv_st[0]; p.a_c = mv_st[1]; p.a_h = mv_st[2]; p.a_w = mv_st[3];
+  p.b_n = mv2_st[0]; p.b_c = mv2_st[1]; p.b_h = mv2_st[2]; p.b_w = mv2_st[3];
+  p.c_n = mv3_st[0]; p.c_c = mv3_st[1]; p.c_h = mv3_st[2]; p.c_w = mv3_st[3];
+  const long long total = (long long)N * 2 * p.H3 * p.W3;
+  flow_pyramid_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("flow_pyramid_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+"""Drop-ins for the CompressAI entropy models the reference constructs:
+
+* ``GaussianConditional(None)``  -- video_model.py:150, :322; called :232, :405
+* ``EntropyBottleneck(channels)`` -- base_model.py:63; called video_model.py:220, :392;
+  ``_get_medians()`` :222, :394; ``loss()`` base_model.py:76
+
+Same constructor arguments, parameter/buffer names (SURVEY.md Appendix B --
+``DMC.load_state_dict`` validates them, video_model.py:626-656), call signature
+``module(x, ...) -> (outputs, likelihoods)`` and training/eval semantics.  The
+forward of each module is ONE kernel of ``libdvc_b200.so`` (the eager original
+is ~20 resp. ~81 launches); the returned likelihood tensor also carries the
+fused per-sample ``sum(ln p)`` as ``likelihoods._dvc_logsum`` which
+``deepvideocodec_b200.rate.collect_likelihoods_list`` consumes so the rate
+never re-reads the likelihoods from HBM.
+
+CUDA fp32 tensors only.  There is no CPU path: a CPU tensor raises.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+
+__all__ = ["EntropyModel", "EntropyBottleneck", "GaussianConditional", "LowerBound"]
+
+
+# ---------------------------------------------------------------------------
+# LowerBound (CompressAI ops.bound_ops) -- kept for state_dict compatibility
+# (``*.likelihood_lower_bound.bound``, ``*.lower_bound_scale.bound``).  The fused
+# kernels apply the bounds themselves; this module is only a holder for them.
+# ---------------------------------------------------------------------------
+class LowerBound(nn.Module):
+    def __init__(self, bound: float):
+        super().__init__()
+        self.register_buffer("bound", torch.Tensor([float(bound)]))
+        self._bound_f = float(np.float32(bound))
+
+    def value(self) -> float:
+        return self._bound_f
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._bound_f = float(self.bound.detach().cpu().reshape(-1)[0])
+
+    def forward(self, x):
+        raise nat.DvcError(
+            "LowerBound is fused into the likelihood kernels of deepvideocodec_b200; "
+            "call GaussianConditional / EntropyBottleneck instead")
+
+
+def _launch_noise_like(x):
+    # CompressAI: torch.empty_like(inputs).uniform_(-0.5, 0.5) from torch's generator
+    return torch.empty_like(x).uniform_(-0.5, 0.5)
+
+
+class EntropyModel(nn.Module):
+    def __init__(self, likelihood_bound: float = 1e-9, entropy_coder=None,
+                 entropy_coder_precision: int = 16):
+        super().__init__()
+        self.entropy_coder = entropy_coder
+        self.entropy_coder_precision = int(entropy_coder_precision)
+        self.use_likelihood_bound = likelihood_bound > 0
+        if self.use_likelihood_bound:
+            self.likelihood_lower_bound = LowerBound(likelihood_bound)
+        self.register_buffer("_offset", torch.IntTensor())
+        self.register_buffer("_quantized_cdf", torch.IntTensor())
+        self.register_buffer("_cdf_length", torch.IntTensor())
+
+    def _lik_bound(self) -> float:
+        # a bound of -inf disables the clamp inside the kernels
+        return self.likelihood_lower_bound.value() if self.use_likelihood_bound else -math.inf
+
+    def forward(self, *args):
+        raise NotImplementedError()
+
+    def quantize(self, inputs, mode, means=None):
+        from .utils import _round_fwd
+        if mode not in ("noise", "dequantize", "symbols"):
+            raise ValueError(f'Invalid quantization mode: "{mode}"')
+        if mode == "noise":
+            return inputs + _launch_noise_like(inputs)
+        shifted = inputs if means is None else inputs - means
+        q = _round_fwd(shifted.contiguous())
+        if mode == "dequantize":
+            return q if means is None else q + means
+        return q.int()
+
+    # real entropy coding: SURVEY.md section 8 rows f1/f2
+    def compress(self, *a, **k):
+        raise NotImplementedError("deepvideocodec_b200: bitstream coding is outside the hot path "
+                                  "(SURVEY.md 8f); estimated rate only")
+
+    def decompress(self, *a, **k):
+        raise NotImplementedError("deepvideocodec_b200: bitstream coding is outside the hot path "
+                                  "(SURVEY.md 8f); estimated rate only")
+
+
+# ---------------------------------------------------------------------------
+# Gaussian conditional
+# ---------------------------------------------------------------------------
+def _gc_fwd(inputs, scales, means, noise, scale_bound, lik_bound, want_outputs=True):
+    n, c, h, w = inputs.shape
+    outputs = torch.empty_like(inputs) if want_outputs else None
+    lik = torch.empty_like(inputs)
+    logsum = torch.empty(n, dtype=torch.float64, device=inputs.device)
+    ws = nat.rate_workspace(inputs.device, n)
+    with nat.device_of(inputs):
+        rc = nat.lib().dvc_gc_likelihood_fwd(
+            inputs.data_ptr(), scales.data_ptr(), nat.ptr(means), nat.ptr(noise),
+            nat.ptr(outputs), lik.data_ptr(), logsum.data_ptr(), ws.data_ptr(), n, c, h, w,
+            nat.st4(inputs), nat.st4(scales), nat.opt_st4(means), nat.opt_st4(noise),
+            nat.st4(lik), scale_bound, lik_bound, nat.stream_of(inputs))
+    nat.check(rc, "dvc_gc_likelihood_fwd")
+    return outputs, lik, logsum
+
+
+class _GaussianConditionalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, scales, means, noise, scale_bound, lik_bound):
+        outputs, lik, logsum = _gc_fwd(inputs, scales, means, noise, scale_bound, lik_bound)
+        ctx.save_for_backward(inputs, scales, means, noise)
+        ctx.bounds = (scale_bound, lik_bound)
+        ctx.mark_non_differentiable(outputs) if noise is None else None
+        return outputs, lik, logsum
+
+    @staticmethod
+    def backward(ctx, g_out, g_lik, g_logsum):
+        inputs, scales, means, noise = ctx.saved_tensors
+        return _gc_bwd(ctx, inputs, scales, means, noise, g_out, g_lik, g_logsum)
+
+
+def _gc_bwd(ctx, inputs, scales, means, noise, g_out, g_lik, g_logsum):
+    from .autograd_kernels import gc_likelihood_bwd
+    gi, gs, gm = gc_likelihood_bwd(inputs, scales, means, noise, g_out, g_lik, g_logsum,
+                                   ctx.bounds[0], ctx.bounds[1], ctx.needs_input_grad[:3])
+    return gi, gs, gm, None, None, None
+
+
+class GaussianConditional(EntropyModel):
+    """``GaussianConditional(scale_table, scale_bound=0.11, tail_mass=1e-9)``."""
+
+    def __init__(self, scale_table, *args, scale_bound=0.11, tail_mass=1e-9, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not isinstance(scale_table, (type(None), list, tuple)):
+            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
+        if scale_table and len(scale_table) < 1:
+            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
+        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
+            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        self.tail_mass = float(tail_mass)
+        if scale_bound is None and scale_table:
+            scale_bound = scale_table[0]
+        if scale_bound <= 0:
+            raise ValueError("Invalid parameters")
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self.register_buffer(
+            "scale_table",
+            torch.Tensor(tuple(float(s) for s in scale_table)) if scale_table else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
+
+    def update_scale_table(self, scale_table, force=False):
+        raise NotImplementedError("deepvideocodec_b200: CDF tables belong to the bitstream path "
+                                  "(SURVEY.md 8f)")
+
+    def build_indexes(self, scales):
+        raise NotImplementedError("deepvideocodec_b200: CDF tables belong to the bitstream path "
+                                  "(SURVEY.md 8f)")
+
+    def forward(self, inputs, scales, means=None, training=None):
+        if training is None:
+            training = self.training
+        inputs = nat.require_cuda_f32(inputs, "GaussianConditional(inputs)")
+        scales = nat.require_cuda_f32(scales, "GaussianConditional(scales)")
+        if scales.shape != inputs.shape:
+            raise nat.DvcError("GaussianConditional: scales must have the shape of inputs")
+        if means is not None:
+            means = nat.require_cuda_f32(means, "GaussianConditional(means)")
+            if means.shape != inputs.shape:
+                raise nat.DvcError("GaussianConditional: means must have the shape of inputs")
+        noise = _launch_noise_like(inputs) if training else None
+        sb, lb = self.lower_bound_scale.value(), self._lik_bound()
+        needs_grad = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (inputs, scales, means))
+        if needs_grad:
+            outputs, lik, logsum = _GaussianConditionalFn.apply(inputs, scales, means, noise, sb, lb)
+        else:
+            outputs, lik, logsum = _gc_fwd(inputs, scales, means, noise, sb, lb)
+        lik._dvc_logsum = logsum
+        return outputs, lik
+
+
+# ---------------------------------------------------------------------------
+# factorised entropy bottleneck
+# ---------------------------------------------------------------------------
+def pack_eb_params(eb):
+    """Concatenate the per-layer parameters into the kernel's per-channel
+    layout: matrices [C,33], biases [C,13], factors [C,12], medians [C].
+    Differentiable (plain ``torch.cat``), so gradients reach the module's own
+    parameters.  Works on any module with CompressAI's attribute names."""
+    c = eb._matrix0.size(0)
+    mats = torch.cat([getattr(eb, f"_matrix{k}").reshape(c, -1) for k in range(5)], dim=1)
+    bias = torch.cat([getattr(eb, f"_bias{k}").reshape(c, -1) for k in range(5)], dim=1)
+    fact = torch.cat([getattr(eb, f"_factor{k}").reshape(c, -1) for k in range(4)], dim=1)
+    med = eb.quantiles[:, 0, 1]
+    if mats.size(1) != 33 or bias.size(1) != 13 or fact.size(1) != 12:
+        raise nat.DvcError("EntropyBottleneck kernel supports filters=(3,3,3,3) only")
+    return mats.contiguous(), bias.contiguous(), fact.contiguous(), med.contiguous()
+
+
+def _packed_cached(eb):
+    """In no-grad mode the packing is cached until a parameter changes."""
+    names = [f"_matrix{k}" for k in range(5)] + [f"_bias{k}" for k in range(5)] + \
+            [f"_factor{k}" for k in range(4)] + ["quantiles"]
+    key = tuple((getattr(eb, n).data_ptr(), getattr(eb, n)._version) for n in names)
+    cache = getattr(eb, "_dvc_packed", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            cache = (key, tuple(t.detach() for t in pack_eb_params(eb)))
+        eb._dvc_packed = cache
+    return cache[1]
+
+
+def _eb_fwd(z, noise, mats, bias, fact, med, lik_bound, want_outputs, want_zhat):
+    n, c, h, w = z.shape
+    outputs = torch.empty_like(z) if want_outputs else None
+    z_hat = torch.empty_like(z) if want_zhat else None
+    lik = torch.empty_like(z)
+    logsum = torch.empty(n, dtype=torch.float64, device=z.device)
+    ws = nat.rate_workspace(z.device, n)
+    with nat.device_of(z):
+        rc = nat.lib().dvc_eb_likelihood_fwd(
+            z.data_ptr(), nat.ptr(noise), mats.data_ptr(), bias.data_ptr(), fact.data_ptr(),
+            med.data_ptr(), nat.ptr(outputs), nat.ptr(z_hat), lik.data_ptr(), logsum.data_ptr(),
+            ws.data_ptr(), n, c, h, w, nat.st4(z), nat.opt_st4(noise), nat.st4(lik),
+            lik_bound, nat.stream_of(z))
+    nat.check(rc, "dvc_eb_likelihood_fwd")
+    return outputs, z_hat, lik, logsum
+
+
+class _EntropyBottleneckFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, noise, mats, bias, fact, med, lik_bound, want_zhat):
+        outputs, z_hat, lik, logsum = _eb_fwd(z, noise, mats, bias, fact, med, lik_bound,
+                                              True, want_zhat)
+        ctx.save_for_backward(z, noise, mats, bias, fact, med)
+        ctx.lik_bound = lik_bound
+        if z_hat is None:
+            z_hat = z.new_empty(0)
+        return outputs, z_hat, lik, logsum
+
+    @staticmethod
+    def backward(ctx, g_out, g_zhat, g_lik, g_logsum):
+        from .autograd_kernels import eb_likelihood_bwd
+        z, noise, mats, bias, fact, med = ctx.saved_tensors
+        gz, gm, gb, gf, gmed = eb_likelihood_bwd(z, noise, mats, bias, fact, med, g_out, g_zhat,
+                                                 g_lik, g_logsum, ctx.lik_bound,
+                                                 ctx.needs_input_grad)
+        return gz, None, gm, gb, gf, gmed, None, None
+
+
+def eb_forward(eb, z, training=None, want_outputs=True, want_zhat=False):
+    """Kernel entry shared by the module and the fused context models.
+    Returns ``(outputs, z_hat, likelihood)``; works for any module exposing
+    CompressAI's EntropyBottleneck attribute names."""
+    if training is None:
+        training = eb.training
+    z = nat.require_cuda_f32(z, "EntropyBottleneck(x)")
+    if z.size(1) != eb._matrix0.size(0):
+        raise nat.DvcError(f"EntropyBottleneck: expected {eb._matrix0.size(0)} channels, "
+                           f"got {z.size(1)}")
+    bound = getattr(eb, "likelihood_lower_bound", None)
+    if not getattr(eb, "use_likelihood_bound", True) or bound is None:
+        lb = -math.inf
+    elif hasattr(bound, "value"):
+        lb = bound.value()
+    else:                                   # real CompressAI LowerBound module
+        lb = getattr(eb, "_dvc_lik_bound", None)
+        if lb is None:
+            lb = float(bound.bound.detach().cpu().reshape(-1)[0])
+            eb._dvc_lik_bound = lb
+    noise = _launch_noise_like(z) if training else None
+    params = [getattr(eb, f"_matrix{k}") for k in range(5)] + [eb.quantiles]
+    needs_grad = torch.is_grad_enabled() and (
+        z.requires_grad or any(p.requires_grad for p in params))
+    if needs_grad:
+        mats, bias, fact, med = pack_eb_params(eb)
+        outputs, z_hat, lik, logsum = _EntropyBottleneckFn.apply(
+            z, noise, mats, bias, fact, med, lb, want_zhat)
+        if not want_zhat:
+            z_hat = None
+    else:
+        mats, bias, fact, med = _packed_cached(eb)
+        outputs, z_hat, lik, logsum = _eb_fwd(z, noise, mats, bias, fact, med, lb,
+                                              want_outputs, want_zhat)
+    lik._dvc_logsum = logsum
+    return outputs, z_hat, lik
+
+
+class EntropyBottleneck(EntropyModel):
+    """``EntropyBottleneck(channels, tail_mass=1e-9, init_scale=10, filters=(3,3,3,3))``."""
+
+    def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3),
+                 **kwargs):
+        super().__init__(*args, **kwargs)
+        self.channels = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        if self.filters != (3, 3, 3, 3):
+            raise NotImplementedError("deepvideocodec_b200 EntropyBottleneck: filters=(3,3,3,3) "
+                                      "only (the sole configuration the reference constructs)")
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        dims = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for k in range(len(self.filters) + 1):
+            init = np.log(np.expm1(1 / scale / dims[k + 1]))
+            matrix = torch.Tensor(self.channels, dims[k + 1], dims[k])
+            matrix.data.fill_(init)
+            self.register_parameter(f"_matrix{k:d}", nn.Parameter(matrix))
+            bias = torch.Tensor(self.channels, dims[k + 1], 1)
+            nn.init.uniform_(bias, -0.5, 0.5)
+            self.register_parameter(f"_bias{k:d}", nn.Parameter(bias))
+            if k < len(self.filters):
+                factor = torch.Tensor(self.channels, dims[k + 1], 1)
+                nn.init.zeros_(factor)
+                self.register_parameter(f"_factor{k:d}", nn.Parameter(factor))
+        self.quantiles = nn.Parameter(torch.Tensor(self.channels, 1, 3))
+        init = torch.Tensor([-self.init_scale, 0, self.init_scale])
+        self.quantiles.data = init.repeat(self.quantiles.size(0), 1, 1)
+        target = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-target, 0, target]))
+
+    def _get_medians(self):
+        return self.quantiles[:, :, 1:2]
+
+    def update(self, force=False):
+        raise NotImplementedError("deepvideocodec_b200: CDF tables belong to the bitstream path "
+                                  "(SURVEY.md 8f)")
+
+    def loss(self):
+        """Auxiliary quantile loss (base_model.py:71-78, train.py:336).  It touches
+        only the [C,1,3] quantiles and the (detached) per-channel parameters --
+        3*C scalars, no data tensor -- so it is plain torch, not a kernel."""
+        import torch.nn.functional as F
+        logits = self.quantiles
+        for k in range(5):
+            logits = torch.matmul(F.softplus(getattr(self, f"_matrix{k}").detach()), logits)
+            logits = logits + getattr(self, f"_bias{k}").detach()
+            if k < 4:
+                logits = logits + torch.tanh(getattr(self, f"_factor{k}").detach()) * torch.tanh(logits)
+        return torch.abs(logits - self.target).sum()
+
+    def forward(self, x, training=None):
+        outputs, _, lik = eb_forward(self, x, training=training, want_outputs=True)
+        return outputs, lik

@@ -1,0 +1,214 @@
+"""Drop-ins for the warp half of the reference's ``dmc/models/layers.py``.
+
+Same names, argument meaning and return structure as the reference:
+
+* ``flow_warp(im, flow)``            -- layers.py:196-198 (``torch_warp`` :175-193)
+* ``bilineardownsacling(x)``         -- layers.py:201-206
+* ``motion_compensation_warps(...)`` -- the non-conv part of
+  ``DMC.motion_compensation`` (video_model.py:497-504) in one launch
+
+Each call is one kernel of ``libdvc_b200.so`` (no grid tensor, no flow
+normalisation passes, no global cache -- the reference's ``backward_grid``
+cache and its CPU/``cuda:7`` aliasing are deliberately not reproduced).
+Both NCHW-contiguous and ``torch.channels_last`` tensors are accepted; the
+output takes the memory format of ``im``.  channels_last with C % 4 == 0 is
+the fast path.
+"""
+import ctypes
+
+import torch
+
+from . import _native as nat
+
+__all__ = ["flow_warp", "torch_warp", "bilineardownsacling", "flow_pyramid",
+           "motion_compensation_warps"]
+
+
+def _check_warp_args(im, flow):
+    nat.require_cuda_f32(im, "flow_warp(im)")
+    nat.require_cuda_f32(flow, "flow_warp(flow)")
+    if flow.device != im.device:
+        raise nat.DvcError("flow_warp: im and flow are on different devices")
+    n, c, h, w = im.shape
+    if flow.shape != (n, 2, h, w):
+        # the reference builds its base grid from the flow's size and samples
+        # `im`; it only ever calls with equal sizes
+        raise nat.DvcError(f"flow_warp: flow must be [N,2,H,W] matching im {tuple(im.shape)}, "
+                           f"got {tuple(flow.shape)}")
+    if h < 2 or w < 2:
+        raise nat.DvcError("flow_warp: H and W must be >= 2")
+
+
+def _warp_fwd(im, flow, flags=0):
+    out = torch.empty_like(im)            # preserves NCHW / channels_last
+    n, c, h, w = im.shape
+    with nat.device_of(im):
+        rc = nat.lib().dvc_flow_warp_fwd(im.data_ptr(), flow.data_ptr(), out.data_ptr(),
+                                         n, c, h, w, nat.st4(im), nat.st4(flow), nat.st4(out),
+                                         flags, nat.stream_of(im))
+    nat.check(rc, "dvc_flow_warp_fwd")
+    return out
+
+
+class _FlowWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, im, flow, flags):
+        ctx.save_for_backward(im, flow)
+        ctx.flags = flags
+        return _warp_fwd(im, flow, flags)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        im, flow = ctx.saved_tensors
+        need_im, need_flow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_out = nat.require_cuda_f32(grad_out, "flow_warp(grad_out)")
+        n, c, h, w = im.shape
+        grad_im = torch.zeros_like(im) if need_im else None
+        grad_flow = torch.empty_like(flow) if need_flow else None
+        with nat.device_of(im):
+            rc = nat.lib().dvc_flow_warp_bwd(
+                grad_out.data_ptr(), im.data_ptr(), flow.data_ptr(), nat.ptr(grad_im),
+                nat.ptr(grad_flow), n, c, h, w, nat.st4(grad_out), nat.st4(im), nat.st4(flow),
+                nat.opt_st4(grad_im), nat.opt_st4(grad_flow), ctx.flags, nat.stream_of(im))
+        nat.check(rc, "dvc_flow_warp_bwd")
+        return grad_im, grad_flow, None
+
+
+def flow_warp(im, flow, *, ieee_div=False):
+    """Backward-warp ``im[N,C,H,W]`` by ``flow[N,2,H,W]`` (pixels; channel 0 = x).
+
+    Bilinear, border padding, ``align_corners=True`` -- reference
+    ``flow_warp`` (layers.py:196).  ``ieee_div=True`` reproduces PyTorch-CPU's
+    true division of the flow instead of PyTorch-CUDA's reciprocal multiply.
+    """
+    _check_warp_args(im, flow)
+    flags = nat.DVC_WARP_IEEE_DIV if ieee_div else 0
+    if torch.is_grad_enabled() and (im.requires_grad or flow.requires_grad):
+        return _FlowWarp.apply(im, flow, flags)
+    return _warp_fwd(im, flow, flags)
+
+
+torch_warp = flow_warp      # layers.py:175 (the reference exposes both names)
+
+
+# ---------------------------------------------------------------------------
+def _down2_fwd(x, post_scale):
+    n, c, h, w = x.shape
+    fmt = torch.channels_last if (x.is_contiguous(memory_format=torch.channels_last)
+                                  and not x.is_contiguous()) else torch.contiguous_format
+    y = torch.empty((n, c, h // 2, w // 2), dtype=x.dtype, device=x.device, memory_format=fmt)
+    with nat.device_of(x):
+        rc = nat.lib().dvc_bilinear_down2_fwd(x.data_ptr(), y.data_ptr(), n, c, h, w,
+                                              nat.st4(x), nat.st4(y), float(post_scale),
+                                              nat.stream_of(x))
+    nat.check(rc, "dvc_bilinear_down2_fwd")
+    return y
+
+
+class _Down2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, post_scale):
+        ctx.shape = tuple(x.shape)
+        ctx.post = post_scale
+        ctx.like = x.new_empty(0)
+        ctx.channels_last = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        return _down2_fwd(x, post_scale)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        grad_y = nat.require_cuda_f32(grad_y, "bilineardownsacling(grad)")
+        n, c, h, w = ctx.shape
+        fmt = torch.channels_last if ctx.channels_last else torch.contiguous_format
+        grad_x = torch.empty(ctx.shape, dtype=grad_y.dtype, device=grad_y.device, memory_format=fmt)
+        with nat.device_of(grad_y):
+            rc = nat.lib().dvc_bilinear_down2_bwd(grad_y.data_ptr(), grad_x.data_ptr(), n, c, h, w,
+                                                  nat.st4(grad_y), nat.st4(grad_x), float(ctx.post),
+                                                  nat.stream_of(grad_y))
+        nat.check(rc, "dvc_bilinear_down2_bwd")
+        return grad_x, None
+
+
+def bilineardownsacling(inputfeature, *, post_scale=1.0):
+    """``F.interpolate(x, (H//2, W//2), 'bilinear', align_corners=False)`` --
+    reference ``bilineardownsacling`` (layers.py:201-206; the spelling is the
+    reference's).  ``post_scale`` folds the ``/ 2`` of video_model.py:499-500."""
+    x = nat.require_cuda_f32(inputfeature, "bilineardownsacling(x)")
+    if x.size(2) < 2 or x.size(3) < 2:
+        raise nat.DvcError("bilineardownsacling: H and W must be >= 2")
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _Down2.apply(x, float(post_scale))
+    return _down2_fwd(x, float(post_scale))
+
+
+def flow_pyramid(mv):
+    """``mv2 = bilineardownsacling(mv) / 2; mv3 = bilineardownsacling(mv2) / 2``
+    (video_model.py:499-500).  One launch when H, W are multiples of 4 and no
+    gradient is needed; two single-level launches otherwise."""
+    mv = nat.require_cuda_f32(mv, "flow_pyramid(mv)")
+    n, c, h, w = mv.shape
+    fused = (c == 2 and h % 4 == 0 and w % 4 == 0
+             and not (torch.is_grad_enabled() and mv.requires_grad))
+    if not fused:
+        mv2 = bilineardownsacling(mv, post_scale=0.5)
+        return mv2, bilineardownsacling(mv2, post_scale=0.5)
+    mv2 = torch.empty((n, 2, h // 2, w // 2), dtype=mv.dtype, device=mv.device)
+    mv3 = torch.empty((n, 2, h // 4, w // 4), dtype=mv.dtype, device=mv.device)
+    with nat.device_of(mv):
+        rc = nat.lib().dvc_flow_pyramid_fwd(mv.data_ptr(), mv2.data_ptr(), mv3.data_ptr(), n, h, w,
+                                            nat.st4(mv), nat.st4(mv2), nat.st4(mv3),
+                                            nat.stream_of(mv))
+    nat.check(rc, "dvc_flow_pyramid_fwd")
+    return mv2, mv3
+
+
+def _task(im, flow, out):
+    t = nat.WarpTask()
+    t.im, t.flow, t.out = im.data_ptr(), flow.data_ptr(), out.data_ptr()
+    t.N, t.C, t.H, t.W = im.shape
+    t.im_st = nat.st4(im)
+    t.flow_st = nat.st4(flow)
+    t.out_st = nat.st4(out)
+    return t
+
+
+def warp_multi(pairs, *, ieee_div=False):
+    """Warp up to 4 independent ``(im, flow)`` pairs in ONE launch (forward
+    only).  Returns the list of warped tensors."""
+    if not 1 <= len(pairs) <= 4:
+        raise nat.DvcError("warp_multi: 1..4 (im, flow) pairs")
+    outs = []
+    tasks = (nat.WarpTask * len(pairs))()
+    for i, (im, flow) in enumerate(pairs):
+        _check_warp_args(im, flow)
+        if im.device != pairs[0][0].device:
+            raise nat.DvcError("warp_multi: all tensors must be on one device")
+        out = torch.empty_like(im)
+        outs.append(out)
+        tasks[i] = _task(im, flow, out)
+    im0 = pairs[0][0]
+    with nat.device_of(im0):
+        rc = nat.lib().dvc_warp_multi_fwd(ctypes.cast(tasks, ctypes.c_void_p), len(pairs),
+                                          nat.DVC_WARP_IEEE_DIV if ieee_div else 0,
+                                          nat.stream_of(im0))
+    nat.check(rc, "dvc_warp_multi_fwd")
+    return outs
+
+
+def motion_compensation_warps(x_ref, feat1, feat2, feat3, mv):
+    """The warps of ``DMC.motion_compensation`` (video_model.py:497-504):
+
+        warpframe = flow_warp(x_ref, mv);  mv2, mv3 = pyramid(mv)
+        context_k = flow_warp(feat_k, mv_k)
+
+    Returns ``(context1, context2, context3, warpframe, mv2, mv3)``.  Two
+    launches in inference (pyramid + one multi-scale warp grid); falls back to
+    the per-op autograd functions when a gradient is required."""
+    need_grad = torch.is_grad_enabled() and any(
+        t.requires_grad for t in (x_ref, feat1, feat2, feat3, mv))
+    mv2, mv3 = flow_pyramid(mv)
+    if need_grad:
+        return (flow_warp(feat1, mv), flow_warp(feat2, mv2), flow_warp(feat3, mv3),
+                flow_warp(x_ref, mv), mv2, mv3)
+    # big task first so the small ones fill the tail of the grid
+    c1, c2, c3, wf = warp_multi([(feat1, mv), (feat2, mv2), (feat3, mv3), (x_ref, mv)])
+    return c1, c2, c3, wf, mv2, mv3

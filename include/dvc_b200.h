@@ -1,0 +1,230 @@
+/*
+ * dvc_b200.h -- C ABI of libdvc_b200.so: the B200 (sm_100a) hot path of the
+ * DMC contextual P-frame codec (lumingzzz/DeepVideoCodec, dmc/models).
+ *
+ * The reference has no FFI: its seam is Python name binding.
+ * Each entry point below therefore names the reference Python function whose
+ * arithmetic it replaces; deepvideocodec_b200/*.py re-creates those Python
+ * names on top of this ABI (ctypes), INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 unless stated otherwise;
+ *  - tensors are logical [N,C,H,W]; `*_st` arguments are ELEMENT strides in
+ *    (N,C,H,W) order, so NCHW-contiguous and channels_last both work.  Fast
+ *    paths need: channel stride 1, C % 4 == 0, 16-byte aligned base and
+ *    strides (channels_last); everything else takes the strided path;
+ *  - the library never allocates, frees or synchronises; all launches go to
+ *    `stream`; every call is CUDA-graph capturable and re-entrant;
+ *  - return value: 0 on success, negative dvc_status on failure; the message
+ *    of the last failure on the calling thread is dvc_last_error_string();
+ *  - nullable arguments are marked [opt].
+ */
+#ifndef DVC_B200_H_
+#define DVC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dvc_stream_t; /* == cudaStream_t */
+
+typedef enum dvc_status {
+  DVC_OK = 0,
+  DVC_ERR_INVALID_ARGUMENT = -1,
+  DVC_ERR_UNSUPPORTED = -2,
+  DVC_ERR_CUDA = -3,
+  DVC_ERR_WORKSPACE = -4
+} dvc_status;
+
+/* flags for the warp entry points */
+enum {
+  /* Divide the flow by (S-1)/2 with an IEEE division, as PyTorch-CPU does.
+   * Default (flag clear) multiplies by the fp32 reciprocal, as PyTorch-CUDA
+   * eager does for `tensor / python_float` -- the two differ in the last bit
+   * of the source coordinate. */
+  DVC_WARP_IEEE_DIV = 1
+};
+
+int dvc_version(void);                     /* MAJOR*10000 + MINOR*100 + PATCH */
+const char* dvc_last_error_string(void);   /* thread local, never NULL */
+/* Number of SMs / compute capability of the current device (diagnostics). */
+int dvc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * Piece 1: warp.  Replaces flow_warp/torch_warp, dmc/models/layers.py:175-198
+ * (linspace base grid + flow/((S-1)/2) + F.grid_sample bilinear/border/
+ * align_corners=True), replayed op for op in fp32.
+ *   im   [N,C,H,W]   flow [N,2,H,W] (pixels; ch0 = x, ch1 = y)   out [N,C,H,W]
+ * ------------------------------------------------------------------------- */
+int dvc_flow_warp_fwd(const float* im, const float* flow, float* out,
+                      int64_t N, int64_t C, int64_t H, int64_t W,
+                      const int64_t im_st[4], const int64_t flow_st[4],
+                      const int64_t out_st[4], int flags, dvc_stream_t stream);
+
+/* Backward of the above (ATen grid_sampler_2d_backward semantics: zero
+ * gradient through the border clip, scatter-add into grad_im).
+ *   grad_im   [opt] [N,C,H,W], MUST be zero-filled by the caller (atomics)
+ *   grad_flow [opt] [N,2,H,W] */
+int dvc_flow_warp_bwd(const float* grad_out, const float* im, const float* flow,
+                      float* grad_im, float* grad_flow,
+                      int64_t N, int64_t C, int64_t H, int64_t W,
+                      const int64_t gout_st[4], const int64_t im_st[4],
+                      const int64_t flow_st[4], const int64_t gim_st[4],
+                      const int64_t gflow_st[4], int flags, dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Flow pyramid.  Replaces bilineardownsacling(x) (layers.py:201-206) followed
+ * by `* post_scale` (video_model.py:499-500 uses / 2 -> post_scale = 0.5).
+ *   x [N,C,H,W] -> y [N,C,H/2,W/2];  any H,W >= 2 (odd sizes use the general
+ *   align_corners=False formula).
+ * ------------------------------------------------------------------------- */
+int dvc_bilinear_down2_fwd(const float* x, float* y, int64_t N, int64_t C,
+                           int64_t H, int64_t W, const int64_t x_st[4],
+                           const int64_t y_st[4], float post_scale,
+                           dvc_stream_t stream);
+int dvc_bilinear_down2_bwd(const float* grad_y, float* grad_x, int64_t N,
+                           int64_t C, int64_t H, int64_t W,
+                           const int64_t gy_st[4], const int64_t gx_st[4],
+                           float post_scale, dvc_stream_t stream);
+/* mv -> (mv/2 downscaled, mv/4 downscaled) in ONE launch; needs H%4==0,W%4==0
+ * (always true after the reference pads to x64, dmc/test.py:75-88). */
+int dvc_flow_pyramid_fwd(const float* mv, float* mv2, float* mv3, int64_t N,
+                         int64_t H, int64_t W, const int64_t mv_st[4],
+                         const int64_t mv2_st[4], const int64_t mv3_st[4],
+                         dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Motion-compensation warps in one launch.  Replaces the non-conv part of
+ * DMC.motion_compensation, dmc/models/video_model.py:497-504: warp x_ref by mv,
+ * feat1 by mv, feat2 by mv2, feat3 by mv3.  mv2/mv3 come from
+ * dvc_flow_pyramid_fwd.  All four problems are tiled into one grid.
+ * ------------------------------------------------------------------------- */
+typedef struct dvc_warp_task {
+  const float* im;
+  const float* flow;
+  float* out;
+  int64_t N, C, H, W;
+  int64_t im_st[4], flow_st[4], out_st[4];
+} dvc_warp_task;
+int dvc_warp_multi_fwd(const dvc_warp_task* tasks /* HOST array */, int n_tasks,
+                       int flags, dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Piece 2: quantisation.  quantize_ste forward, dmc/models/utils.py:149-152
+ * (round half to even).  [opt] offset[C] implements the hyper-latent form
+ * z_hat = round(z - med_c) + med_c (video_model.py:222-224); pass NULL for the
+ * plain round.  offset_st is the element stride between channels of `offset`.
+ * ------------------------------------------------------------------------- */
+int dvc_quantize_fwd(const float* x, const float* offset, float* q, int64_t N,
+                     int64_t C, int64_t H, int64_t W, const int64_t x_st[4],
+                     int64_t offset_st, const int64_t q_st[4],
+                     dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Checkerboard dual prior, stage A.  Replaces video_model.py:176-189 (==
+ * :348-361): writes the spatial-prior conv input
+ *   params[N,3C,H,W] = cat(y_hat_00, y_hat_11, means, scales).
+ * ------------------------------------------------------------------------- */
+int dvc_dual_prior_stage_a_fwd(const float* y, const float* means,
+                               const float* scales, float* params, int64_t N,
+                               int64_t C, int64_t H, int64_t W,
+                               const int64_t y_st[4], const int64_t means_st[4],
+                               const int64_t scales_st[4],
+                               const int64_t params_st[4], dvc_stream_t stream);
+
+/* Rate accumulation workspace: one per likelihood kernel launch in flight.
+ * Layout: double partial[DVC_RATE_MAX_BLOCKS * N] followed by uint32 ticket[N]
+ * (the ticket words must be zero before first use; kernels reset them). */
+#define DVC_RATE_MAX_BLOCKS 1024
+int64_t dvc_rate_workspace_bytes(int64_t N);
+
+/* ---------------------------------------------------------------------------
+ * Stage B + Gaussian conditional + rate partial.  Replaces
+ * video_model.py:192-207 (stage B + merge), the GaussianConditional call at
+ * :232 / :405 (CompressAI GaussianConditional.forward: quantise, |v|, scale
+ * lower bound, erfc CDF difference, likelihood lower bound) and the
+ * log(p).sum(dim=(1,2,3)) of dmc/train.py:83.
+ *   y, means, scales [N,C,H,W]; prior [N,2C,H,W] = y_spatial_prior(params)
+ *   noise  [opt] [N,C,H,W] U(-1/2,1/2): training-mode likelihood on y+noise
+ *   y_hat, means_hat, scales_hat, lik [opt] [N,C,H,W]
+ *   q_w0,q_w1,s_w0,s_w1 [opt] [N,C/2,H,W]  (mode='compress', :209-214)
+ *   logsum [opt] double[N]  = sum over C,H,W of ln(lik); needs `workspace`
+ * ------------------------------------------------------------------------- */
+int dvc_dual_prior_stage_b_gc_fwd(
+    const float* y, const float* means, const float* scales, const float* prior,
+    const float* noise, float* y_hat, float* means_hat, float* scales_hat,
+    float* lik, float* q_w0, float* q_w1, float* s_w0, float* s_w1,
+    double* logsum, void* workspace, int64_t N, int64_t C, int64_t H, int64_t W,
+    const int64_t y_st[4], const int64_t means_st[4], const int64_t scales_st[4],
+    const int64_t prior_st[4], const int64_t noise_st[4],
+    const int64_t out_st[4] /* y_hat, means_hat, scales_hat, lik */,
+    const int64_t half_st[4] /* q_w*, s_w* */, float scale_bound,
+    float likelihood_bound, dvc_stream_t stream);
+
+/* Module-level Gaussian conditional (no dual prior).  Replaces CompressAI
+ * GaussianConditional.forward(inputs, scales, means, training).
+ *   means [opt]; noise [opt] (training);  outputs [opt]; lik [opt]; logsum [opt] */
+int dvc_gc_likelihood_fwd(const float* inputs, const float* scales,
+                          const float* means, const float* noise, float* outputs,
+                          float* lik, double* logsum, void* workspace, int64_t N,
+                          int64_t C, int64_t H, int64_t W, const int64_t in_st[4],
+                          const int64_t scales_st[4], const int64_t means_st[4],
+                          const int64_t noise_st[4], const int64_t out_st[4],
+                          float scale_bound, float likelihood_bound,
+                          dvc_stream_t stream);
+/* grad_lik [N,C,H,W] -> grad_inputs, grad_scales, grad_means (all [opt]).
+ * LowerBound rule: pass iff (x >= bound) or (grad < 0).  In eval mode the
+ * rounding has zero gradient, so only grad_scales is non-zero through `lik`;
+ * with noise the gradient flows to inputs and means as well. */
+int dvc_gc_likelihood_bwd(const float* grad_lik, const float* inputs,
+                          const float* scales, const float* means,
+                          const float* noise, float* grad_inputs,
+                          float* grad_scales, float* grad_means, int64_t N,
+                          int64_t C, int64_t H, int64_t W, const int64_t st[4],
+                          float scale_bound, float likelihood_bound,
+                          dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Factorised entropy bottleneck.  Replaces CompressAI EntropyBottleneck.forward
+ * (call sites video_model.py:220, :392) fused with the z quantisation of
+ * :222-224 and the rate partial.  Parameters are the module's own tensors:
+ *   matrices  float[C*33]  (_matrix0..4 concatenated per channel: 3,9,9,9,3)
+ *   biases    float[C*13]  (_bias0..4: 3,3,3,3,1)
+ *   factors   float[C*12]  (_factor0..3: 3 each)
+ *   medians   float[C]     (quantiles[:,0,1])
+ * i.e. filters=(3,3,3,3) (the only configuration the reference constructs).
+ *   z [N,C,H,W]; noise [opt]; outputs [opt] (= z+noise or round(z-med)+med);
+ *   z_hat [opt] (= round(z-med)+med always); lik [opt]; logsum [opt].
+ * ------------------------------------------------------------------------- */
+int dvc_eb_likelihood_fwd(const float* z, const float* noise,
+                          const float* matrices, const float* biases,
+                          const float* factors, const float* medians,
+                          float* outputs, float* z_hat, float* lik,
+                          double* logsum, void* workspace, int64_t N, int64_t C,
+                          int64_t H, int64_t W, const int64_t z_st[4],
+                          const int64_t noise_st[4], const int64_t out_st[4],
+                          float likelihood_bound, dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Piece 4: rate.  Replaces collect_likelihoods_list, dmc/train.py:74-93.
+ *   logsums  double[K*N]  K per-tensor ln-likelihood sums (from the kernels
+ *            above, or from dvc_log_sum_fwd for a likelihood tensor)
+ *   bpp      float[K*N]   = logsum / (-ln2 * num_pixels)
+ *   bpp_total float[N]    = sum over K (left to right, as train.py:85)
+ *   bits     [opt] double[N] = -sum_k logsum / ln2   (bits per sample)
+ * ------------------------------------------------------------------------- */
+int dvc_rate_finalize(const double* logsums, int K, int64_t N,
+                      double num_pixels, float* bpp, float* bpp_total,
+                      double* bits, dvc_stream_t stream);
+/* log(p).sum(dim=(1,2,3)) of an arbitrary likelihood tensor (module boundary,
+ * when the likelihood was not produced by one of the fused kernels). */
+int dvc_log_sum_fwd(const float* lik, double* logsum, void* workspace,
+                    int64_t N, int64_t C, int64_t H, int64_t W,
+                    const int64_t lik_st[4], dvc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVC_B200_H_ */
