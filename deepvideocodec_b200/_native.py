@@ -88,7 +88,8 @@ class WarpTask(ctypes.Structure):
     """Mirror of ``dvc_warp_task`` (include/dvc_b200.h)."""
     _fields_ = [("im", c_void_p), ("flow", c_void_p), ("out", c_void_p),
                 ("N", c_int64), ("C", c_int64), ("H", c_int64), ("W", c_int64),
-                ("im_st", _I64x4), ("flow_st", _I64x4), ("out_st", _I64x4)]
+                ("im_st", _I64x4), ("flow_st", _I64x4), ("out_st", _I64x4),
+                ("flow_downscale", c_int64)]
 
 
 def lib():

@@ -94,7 +94,7 @@ __device__ __forceinline__ float blend(float vnw, float vne, float vsw, float vs
 // ---------------------------------------------------------------------------
 // task descriptors (passed by value as a __grid_constant__)
 // ---------------------------------------------------------------------------
-enum { kModeVec4 = 0, kModeStrided = 1 };
+enum { kModeVec4 = 0, kModeStrided = 1, kModeVec4C64 = 2 };
 constexpr int kThreads = 256;
 constexpr int kRows = 8;         // tile height of both paths
 constexpr int kStridedTileW = 32;
@@ -111,7 +111,9 @@ struct WarpTask {
   long long out_n, out_c, out_h, out_w;
   int mode;
   int c4;            // vec4: float4 groups per pixel
-  int ppb;           // vec4: pixels per tile row = kThreads / c4
+  int ppb;           // pixel columns per CTA tile
+  int rows;          // rows per CTA tile
+  int flow_level;    // 0: flow has im's resolution; k: flow is 2^k finer, reduced on the fly
   int tiles_x, tiles_y;
   int first_block, n_blocks;
 };
@@ -121,70 +123,153 @@ struct WarpBatch {
 };
 
 // ---------------------------------------------------------------------------
-// NHWC float4 path
+// flow fetch, optionally through the reference's flow pyramid
+//   level 1: bilineardownsacling(mv) / 2          (video_model.py:499)
+//   level 2: bilineardownsacling(level 1) / 2     (video_model.py:500)
+// evaluated per sample with exactly the arithmetic of flow_pyramid_kernel, so
+// warping with flow_level = k is bit-identical to warping with the
+// materialised mv2 / mv3.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float down2_at(const float* __restrict__ q, long long sh,
+                                          long long sw) {
+  const float a = __ldg(q), b = __ldg(q + sw);
+  const float c = __ldg(q + sh), d = __ldg(q + sh + sw);
+  return mul_rn(mul_rn(add_rn(add_rn(a, b), add_rn(c, d)), 0.25f), 0.5f);
+}
+
+__device__ __forceinline__ float fetch_flow(const float* __restrict__ plane, long long sh,
+                                            long long sw, int h, int w, int level) {
+  if (level == 0) return __ldg(plane + h * sh + w * sw);
+  if (level == 1) return down2_at(plane + (2 * h) * sh + (2 * w) * sw, sh, sw);
+  const float* q = plane + (4 * h) * sh + (4 * w) * sw;
+  const float m00 = down2_at(q, sh, sw), m01 = down2_at(q + 2 * sw, sh, sw);
+  const float m10 = down2_at(q + 2 * sh, sh, sw), m11 = down2_at(q + 2 * sh + 2 * sw, sh, sw);
+  return mul_rn(mul_rn(add_rn(add_rn(m00, m01), add_rn(m10, m11)), 0.25f), 0.5f);
+}
+
+// ---------------------------------------------------------------------------
+// NHWC float4 path -- warp-private tiles, no block barrier
+//
+// A pixel's C channels are C/4 = c4 lanes of one warp (c4 divides 32), so a
+// warp covers ppw = 32/c4 adjacent pixel columns and walks c4 rows: 32 pixels.
+//   phase 1: each lane computes the source coordinate of ONE of those 32
+//            pixels (column lane/c4, row lane%c4) and parks (nw-tap offset +
+//            border flags, 4 weights) in the warp's slice of shared memory;
+//   phase 2: lane = (column, 4-channel group); per row: 2 broadcast LDS,
+//            4 x LDG.128 (the east taps are an immediate offset when the
+//            pixel stride is dense), 16 FFMA, 1 streaming STG.128; two rows
+//            (8 gathers) are in flight per lane.
+// Only __syncwarp separates the phases, so the 8 warps of a CTA (8*ppw columns
+// side by side, sharing source rows through L1) never wait for each other.
+//
+// History (ncu, 1080p motion-compensation launch, 1.49 GB algorithmic):
+//   v1 coordinates recomputed in all c4 lanes        387 us, 236 M warp-inst, issue 55%
+//   v2 taps in smem, CTA barrier, 8-row tiles        307 us, 144 M warp-inst, barrier+long-sb stalls
+//   v3 this version: see profiles/
+// ---------------------------------------------------------------------------
+struct TapSmem {
+  float4 wgt[kThreads];  // nw, ne, sw, se
+  int pos[kThreads];     // float4 offset of the nw tap | east-in << 30 | south-in << 31
+};
+
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
-__device__ __forceinline__ void warp_tile_vec4(const WarpTask& t, int tile) {
+__device__ __forceinline__ float4 blend4(const float4& a, const float4& b, const float4& c,
+                                         const float4& d, const float4& w) {
+  float4 o;
+  o.x = fmaf(d.x, w.w, fmaf(c.x, w.z, fmaf(b.x, w.y, mul_rn(a.x, w.x))));
+  o.y = fmaf(d.y, w.w, fmaf(c.y, w.z, fmaf(b.y, w.y, mul_rn(a.y, w.x))));
+  o.z = fmaf(d.z, w.w, fmaf(c.z, w.z, fmaf(b.z, w.y, mul_rn(a.z, w.x))));
+  o.w = fmaf(d.w, w.w, fmaf(c.w, w.z, fmaf(b.w, w.y, mul_rn(a.w, w.x))));
+  return o;
+}
+
+constexpr unsigned kEastIn = 1u << 30, kSouthIn = 1u << 31, kOffMask = (1u << 30) - 1u;
+
+// gather the 4 taps of one pixel row; `east` is the float4 distance to the
+// east neighbour (compile-time constant in the dense specialisation)
+__device__ __forceinline__ void gather4(const float4* __restrict__ north,
+                                        const float4* __restrict__ south, unsigned pos,
+                                        int east, bool all_in, float4& v0, float4& v1,
+                                        float4& v2, float4& v3) {
+  const unsigned o = pos & kOffMask;
+  if (all_in) {
+    v0 = ldg4(north + o);
+    v1 = ldg4(north + o + east);
+    v2 = ldg4(south + o);
+    v3 = ldg4(south + o + east);
+  } else {  // border: ATen skips out-of-bounds taps (their weight is 0 anyway)
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
+    v0 = ldg4(north + o);
+    v1 = e ? ldg4(north + o + east) : z;
+    v2 = sth ? ldg4(south + o) : z;
+    v3 = (e && sth) ? ldg4(south + o + east) : z;
+  }
+}
+
+template <int C4T>  // C4T = 16: C = 64 with dense pixels; 0: runtime c4
+__device__ __forceinline__ void warp_tile_vec4(const WarpTask& t, int tile, TapSmem& sm) {
+  const int c4 = C4T ? C4T : t.c4;
+  const int ppw = 32 / c4;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int H = t.g.H, W = t.g.W;
   const int tx = tile % t.tiles_x;
   const int rest = tile / t.tiles_x;
   const int ty = rest % t.tiles_y;
   const int n = rest / t.tiles_y;
-
-  const int px = threadIdx.x / t.c4;
-  const int lane = threadIdx.x - px * t.c4;
-  const int w = tx * t.ppb + px;
-  if (px >= t.ppb || w >= t.g.W) return;
-  const int h0 = ty * kRows;
-
+  const int w0 = (tx * (kThreads / 32) + wid) * ppw, h0 = ty * c4;
+  if (w0 >= W) return;  // warp-uniform: no CTA barrier below
   // strides in float4 units (dispatcher guarantees divisibility and int32 range)
-  const int im_h4 = (int)(t.im_h >> 2), im_w4 = (int)(t.im_w >> 2);
-  const float4* __restrict__ im4 = reinterpret_cast<const float4*>(t.im + n * t.im_n) + lane;
-  float4* __restrict__ out4 =
-      reinterpret_cast<float4*>(t.out + n * t.out_n + (long long)w * t.out_w) + lane;
-  const float* __restrict__ fl = t.flow + n * t.fl_n + (long long)w * t.fl_w;
+  const int im_h4 = (int)(t.im_h >> 2);
+  const int im_w4 = C4T ? C4T : (int)(t.im_w >> 2);
 
-  // the flow of the whole tile column first: 2*kRows independent loads in flight
-  float fx[kRows], fy[kRows];
-#pragma unroll
-  for (int r = 0; r < kRows; ++r) {
-    const int h = min(h0 + r, t.g.H - 1);
-    fx[r] = __ldg(fl + h * t.fl_h);
-    fy[r] = __ldg(fl + h * t.fl_h + t.fl_c);
+  // ---- phase 1: one tap record per lane --------------------------------------
+  {
+    const int pc = lane / c4, r = lane - pc * c4;
+    const int h = min(h0 + r, H - 1), w = min(w0 + pc, W - 1);
+    const float* __restrict__ fl = t.flow + n * t.fl_n;
+    const float fx = fetch_flow(fl, t.fl_h, t.fl_w, h, w, t.flow_level);
+    const float fy = fetch_flow(fl + t.fl_c, t.fl_h, t.fl_w, h, w, t.flow_level);
+    const Taps T = make_taps(t.g, h, w, fx, fy);
+    sm.wgt[threadIdx.x] = make_float4(T.nw, T.ne, T.sw, T.se);
+    sm.pos[threadIdx.x] = (int)((unsigned)(T.y0 * im_h4 + T.x0 * im_w4) |
+                                (T.dx ? kEastIn : 0u) | (T.dy ? kSouthIn : 0u));
   }
+  __syncwarp();
 
-#pragma unroll
-  for (int r = 0; r < kRows; r += 2) {
-    const int hA = h0 + r, hB = hA + 1;
-    if (hA >= t.g.H) break;
-    const bool okB = hB < t.g.H;
-    const Taps A = make_taps(t.g, hA, w, fx[r], fy[r]);
-    const Taps B = make_taps(t.g, okB ? hB : hA, w, fx[r + 1], fy[r + 1]);
-    const int oA = A.y0 * im_h4 + A.x0 * im_w4;
-    const int oB = B.y0 * im_h4 + B.x0 * im_w4;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    // 8 independent 128-bit gathers before the first use
-    const float4 a_nw = ldg4(im4 + oA);
-    const float4 a_ne = A.dx ? ldg4(im4 + oA + im_w4) : z;
-    const float4 a_sw = A.dy ? ldg4(im4 + oA + im_h4) : z;
-    const float4 a_se = (A.dx & A.dy) ? ldg4(im4 + oA + im_h4 + im_w4) : z;
-    const float4 b_nw = ldg4(im4 + oB);
-    const float4 b_ne = B.dx ? ldg4(im4 + oB + im_w4) : z;
-    const float4 b_sw = B.dy ? ldg4(im4 + oB + im_h4) : z;
-    const float4 b_se = (B.dx & B.dy) ? ldg4(im4 + oB + im_h4 + im_w4) : z;
-    float4 o;
-    o.x = blend(a_nw.x, a_ne.x, a_sw.x, a_se.x, A);
-    o.y = blend(a_nw.y, a_ne.y, a_sw.y, a_se.y, A);
-    o.z = blend(a_nw.z, a_ne.z, a_sw.z, a_se.z, A);
-    o.w = blend(a_nw.w, a_ne.w, a_sw.w, a_se.w, A);
-    st_streaming(out4 + ((long long)hA * t.out_h >> 2), o);
-    if (okB) {
-      o.x = blend(b_nw.x, b_ne.x, b_sw.x, b_se.x, B);
-      o.y = blend(b_nw.y, b_ne.y, b_sw.y, b_se.y, B);
-      o.z = blend(b_nw.z, b_ne.z, b_sw.z, b_se.z, B);
-      o.w = blend(b_nw.w, b_ne.w, b_sw.w, b_se.w, B);
-      st_streaming(out4 + ((long long)hB * t.out_h >> 2), o);
-    }
+  // ---- phase 2: gather + blend -----------------------------------------------
+  const int px = lane / c4, grp = lane - px * c4;
+  const int w = w0 + px;
+  if (w >= W) return;
+  const float4* __restrict__ north = reinterpret_cast<const float4*>(t.im + n * t.im_n) + grp;
+  const float4* __restrict__ south = north + im_h4;
+  const long long out_h4 = t.out_h >> 2;
+  float4* __restrict__ out4 =
+      reinterpret_cast<float4*>(t.out + n * t.out_n + (long long)w * t.out_w) + grp +
+      h0 * out_h4;
+  const int rows = min(c4, H - h0);
+  const float4* __restrict__ wgt = sm.wgt + (wid << 5) + px * c4;
+  const int* __restrict__ pos = sm.pos + (wid << 5) + px * c4;
+
+  int r = 0;
+#pragma unroll 1
+  for (; r + 2 <= rows; r += 2) {
+    const unsigned pa = (unsigned)pos[r], pb = (unsigned)pos[r + 1];
+    const float4 wa = wgt[r], wb = wgt[r + 1];
+    const bool all_in = ((pa & pb) >> 30) == 3u;
+    float4 a0, a1, a2, a3, b0, b1, b2, b3;
+    gather4(north, south, pa, im_w4, all_in, a0, a1, a2, a3);
+    gather4(north, south, pb, im_w4, all_in, b0, b1, b2, b3);
+    st_streaming(out4, blend4(a0, a1, a2, a3, wa));
+    st_streaming(out4 + out_h4, blend4(b0, b1, b2, b3, wb));
+    out4 += 2 * out_h4;
+  }
+  if (r < rows) {
+    const unsigned pa = (unsigned)pos[r];
+    float4 a0, a1, a2, a3;
+    gather4(north, south, pa, im_w4, false, a0, a1, a2, a3);
+    st_streaming(out4, blend4(a0, a1, a2, a3, wgt[r]));
   }
 }
 
@@ -200,8 +285,9 @@ __device__ __forceinline__ void warp_tile_strided(const WarpTask& t, int tile) {
   const int h = ty * kRows + (threadIdx.x >> 5);
   if (w >= t.g.W || h >= t.g.H) return;
 
-  const float* __restrict__ fl = t.flow + n * t.fl_n + h * t.fl_h + w * t.fl_w;
-  const float fx = __ldg(fl), fy = __ldg(fl + t.fl_c);
+  const float* __restrict__ fl = t.flow + n * t.fl_n;
+  const float fx = fetch_flow(fl, t.fl_h, t.fl_w, h, w, t.flow_level);
+  const float fy = fetch_flow(fl + t.fl_c, t.fl_h, t.fl_w, h, w, t.flow_level);
   const Taps T = make_taps(t.g, h, w, fx, fy);
 
   const float* __restrict__ p_nw = t.im + n * t.im_n + T.y0 * t.im_h + T.x0 * t.im_w;
@@ -235,8 +321,11 @@ warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
     if (i < batch.n_tasks && b >= batch.t[i].first_block) k = i;
   const WarpTask& t = batch.t[k];
   const int tile = b - t.first_block;
-  if (t.mode == kModeVec4)
-    warp_tile_vec4(t, tile);
+  __shared__ TapSmem sm;
+  if (t.mode == kModeVec4C64)
+    warp_tile_vec4<16>(t, tile, sm);
+  else if (t.mode == kModeVec4)
+    warp_tile_vec4<0>(t, tile, sm);
   else
     warp_tile_strided(t, tile);
 }
@@ -264,6 +353,9 @@ static int fill_geom(WarpGeom& g, int64_t H, int64_t W, int flags) {
 
 static int build_task(WarpTask& t, const dvc_warp_task& in, int flags) {
   DVC_REQUIRE(in.im && in.flow && in.out, "flow_warp: null pointer");
+  DVC_REQUIRE(in.flow_downscale >= 0 && in.flow_downscale <= 2,
+              "flow_warp: flow_downscale must be 0, 1 or 2");
+  t.flow_level = in.flow_downscale;
   DVC_REQUIRE(in.N > 0 && in.C > 0 && in.H > 0 && in.W > 0, "flow_warp: empty tensor");
   DVC_REQUIRE(in.H < (1 << 24) && in.W < (1 << 24) && in.N < 65536 && in.C < (1 << 24),
               "flow_warp: extent too large");
@@ -278,21 +370,26 @@ static int build_task(WarpTask& t, const dvc_warp_task& in, int flags) {
   t.im_n = si.n; t.im_c = si.c; t.im_h = si.h; t.im_w = si.w;
   t.fl_n = sf.n; t.fl_c = sf.c; t.fl_h = sf.h; t.fl_w = sf.w;
   t.out_n = so.n; t.out_c = so.c; t.out_h = so.h; t.out_w = so.w;
+  // float4 path: channels_last, c4 = C/4 lanes per pixel must divide a warp
+  const int64_t c4 = in.C / 4;
   const bool vec = nhwc_vec4_ok(in.im, si, in.C) && nhwc_vec4_ok(in.out, so, in.C) &&
-                   in.C / 4 <= kThreads && fits_int32(1, in.C, in.H, in.W, si) &&
-                   si.h >= 0 && si.w >= 0;
+                   c4 >= 1 && c4 <= 32 && (32 % c4) == 0 &&
+                   fits_int32(1, in.C, in.H, in.W, si) && si.h >= 0 && si.w >= 0 &&
+                   (long long)in.H * si.h + (long long)in.W * si.w < (1LL << 32);
   if (vec) {
-    t.mode = kModeVec4;
-    t.c4 = (int)(in.C / 4);
-    t.ppb = kThreads / t.c4;
+    t.mode = (in.C == 64 && si.w == 64) ? kModeVec4C64 : kModeVec4;
+    t.c4 = (int)c4;
+    t.ppb = (kThreads / 32) * (32 / t.c4);   // pixel columns per CTA
+    t.rows = t.c4;                           // rows per CTA (= rows per warp tile)
     t.tiles_x = (int)((in.W + t.ppb - 1) / t.ppb);
   } else {
     t.mode = kModeStrided;
     t.c4 = 0;
     t.ppb = kStridedTileW;
+    t.rows = kRows;
     t.tiles_x = (int)((in.W + kStridedTileW - 1) / kStridedTileW);
   }
-  t.tiles_y = (int)((in.H + kRows - 1) / kRows);
+  t.tiles_y = (int)((in.H + t.rows - 1) / t.rows);
   const long long nb = (long long)t.tiles_x * t.tiles_y * in.N;
   DVC_REQUIRE(nb < 2147483647LL, "flow_warp: too many tiles");
   t.n_blocks = (int)nb;
@@ -430,6 +527,7 @@ int dvc_flow_warp_fwd(const float* im, const float* flow, float* out, int64_t N,
   dvc_warp_task t;
   t.im = im; t.flow = flow; t.out = out;
   t.N = N; t.C = C; t.H = H; t.W = W;
+  t.flow_downscale = 0;
   for (int i = 0; i < 4; ++i) {
     t.im_st[i] = im_st[i];
     t.flow_st[i] = flow_st[i];

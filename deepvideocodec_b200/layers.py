@@ -161,30 +161,45 @@ def flow_pyramid(mv):
     return mv2, mv3
 
 
-def _task(im, flow, out):
+def _task(im, flow, out, level=0):
     t = nat.WarpTask()
     t.im, t.flow, t.out = im.data_ptr(), flow.data_ptr(), out.data_ptr()
     t.N, t.C, t.H, t.W = im.shape
     t.im_st = nat.st4(im)
     t.flow_st = nat.st4(flow)
     t.out_st = nat.st4(out)
+    t.flow_downscale = level
     return t
 
 
 def warp_multi(pairs, *, ieee_div=False):
-    """Warp up to 4 independent ``(im, flow)`` pairs in ONE launch (forward
-    only).  Returns the list of warped tensors."""
+    """Warp up to 4 independent ``(im, flow[, level])`` problems in ONE launch
+    (forward only).  ``level`` k in {0,1,2}: ``flow`` is the motion field at 2^k
+    times the resolution of ``im`` and is reduced on the fly with the
+    reference's pyramid arithmetic (``bilineardownsacling(.) / 2`` k times,
+    video_model.py:499-500).  Returns the list of warped tensors."""
     if not 1 <= len(pairs) <= 4:
         raise nat.DvcError("warp_multi: 1..4 (im, flow) pairs")
     outs = []
     tasks = (nat.WarpTask * len(pairs))()
-    for i, (im, flow) in enumerate(pairs):
-        _check_warp_args(im, flow)
-        if im.device != pairs[0][0].device:
+    for i, item in enumerate(pairs):
+        im, flow = item[0], item[1]
+        level = item[2] if len(item) > 2 else 0
+        if level not in (0, 1, 2):
+            raise nat.DvcError("warp_multi: level must be 0, 1 or 2")
+        nat.require_cuda_f32(im, "warp_multi(im)")
+        nat.require_cuda_f32(flow, "warp_multi(flow)")
+        n, c, h, w = im.shape
+        if flow.shape != (n, 2, h << level, w << level):
+            raise nat.DvcError(f"warp_multi: flow must be {(n, 2, h << level, w << level)} for im "
+                               f"{tuple(im.shape)} at level {level}, got {tuple(flow.shape)}")
+        if h < 2 or w < 2:
+            raise nat.DvcError("warp_multi: H and W must be >= 2")
+        if im.device != pairs[0][0].device or flow.device != im.device:
             raise nat.DvcError("warp_multi: all tensors must be on one device")
         out = torch.empty_like(im)
         outs.append(out)
-        tasks[i] = _task(im, flow, out)
+        tasks[i] = _task(im, flow, out, level)
     im0 = pairs[0][0]
     with nat.device_of(im0):
         rc = nat.lib().dvc_warp_multi_fwd(ctypes.cast(tasks, ctypes.c_void_p), len(pairs),
@@ -200,15 +215,20 @@ def motion_compensation_warps(x_ref, feat1, feat2, feat3, mv):
         warpframe = flow_warp(x_ref, mv);  mv2, mv3 = pyramid(mv)
         context_k = flow_warp(feat_k, mv_k)
 
-    Returns ``(context1, context2, context3, warpframe, mv2, mv3)``.  Two
-    launches in inference (pyramid + one multi-scale warp grid); falls back to
-    the per-op autograd functions when a gradient is required."""
+    Returns ``(context1, context2, context3, warpframe)``.  In inference this
+    is ONE launch: ``mv2``/``mv3`` are intermediates of the reference function
+    and are evaluated inside the warp kernel (bit-identical to materialising
+    them).  When a gradient is required it composes the per-op autograd
+    functions instead."""
     need_grad = torch.is_grad_enabled() and any(
         t.requires_grad for t in (x_ref, feat1, feat2, feat3, mv))
-    mv2, mv3 = flow_pyramid(mv)
-    if need_grad:
+    fusable = (mv.size(2) % 4 == 0 and mv.size(3) % 4 == 0
+               and feat2.shape[-2:] == (mv.size(2) // 2, mv.size(3) // 2)
+               and feat3.shape[-2:] == (mv.size(2) // 4, mv.size(3) // 4))
+    if need_grad or not fusable:
+        mv2, mv3 = flow_pyramid(mv)
         return (flow_warp(feat1, mv), flow_warp(feat2, mv2), flow_warp(feat3, mv3),
-                flow_warp(x_ref, mv), mv2, mv3)
+                flow_warp(x_ref, mv))
     # big task first so the small ones fill the tail of the grid
-    c1, c2, c3, wf = warp_multi([(feat1, mv), (feat2, mv2), (feat3, mv3), (x_ref, mv)])
-    return c1, c2, c3, wf, mv2, mv3
+    c1, c2, c3, wf = warp_multi([(feat1, mv, 0), (feat2, mv, 1), (feat3, mv, 2), (x_ref, mv, 0)])
+    return c1, c2, c3, wf

@@ -50,9 +50,9 @@ def install_compressai_shim(force=False):
 
 def _motion_compensation(self, mv, dpb):
     """Drop-in for ``DMC.motion_compensation`` (video_model.py:497-506): the
-    flow pyramid is one launch and the four warps are one launch."""
+    flow pyramid and the four warps are ONE launch."""
     ref_feature1, ref_feature2, ref_feature3 = self.multi_scale_feature_extractor(dpb)
-    context1, context2, context3, warpframe, _, _ = layers.motion_compensation_warps(
+    context1, context2, context3, warpframe = layers.motion_compensation_warps(
         dpb["x_ref"], ref_feature1, ref_feature2, ref_feature3, mv)
     context1, context2, context3 = self.context_fusion_net(context1, context2, context3)
     return context1, context2, context3, warpframe

@@ -1,0 +1,264 @@
+"""One P-frame of the hot path on resident tensors, with preallocated outputs.
+
+This is the region BASELINE.json's metric is quoted on (SURVEY.md 8d "timed
+region"): per P-frame
+
+    flow pyramid (mv -> mv2, mv3; evaluated inside the warp) video_model.py:499-500
+    warp x_ref, feat1, feat2, feat3 (ONE launch)            video_model.py:498, 502-504
+    for both context models (motion, frame):
+        entropy bottleneck likelihood + z_hat               video_model.py:220-224 / 392-396
+        dual prior stage A -> spatial-prior conv input      video_model.py:176-189 / 348-361
+        dual prior stage B + Gaussian conditional + ln-sum  video_model.py:192-207, 232 / 364-379, 405
+    rate finalise (bits, bpp)                               train.py:74-93
+
+The convolutions between those steps are outside the path; their outputs are
+inputs here.  ``PFramePath`` binds one set of input tensors, allocates every
+output once, pre-builds the C-ABI argument lists and then ``launch()`` only
+enqueues kernels: no allocation, no host sync, CUDA-graph capturable.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _native as nat
+from .entropy_models import _packed_cached
+
+__all__ = ["PFramePath", "synthetic_pframe_inputs", "pframe_algorithmic_bytes"]
+
+
+def pframe_algorithmic_bytes(h, w, n=1, c_feat=64, c_mv=64, c_y=96, c_z=64):
+    """Algorithmic bytes of one P-frame: fp32, every operand
+    read once and every result written once."""
+    def warp(c, hh, ww):
+        return 4 * n * hh * ww * (2 * c + 2)
+    pyr = 4 * n * 2 * (h * w + h * w // 4) + 4 * n * 2 * (h * w // 4 + h * w // 16)
+    lh, lw = h // 16, w // 16
+    zh, zw = h // 64, w // 64
+    d = {
+        "warp_x_ref": warp(3, h, w),
+        "warp_ctx1": warp(c_feat, h, w),
+        "warp_ctx2": warp(c_feat, h // 2, w // 2),
+        "warp_ctx3": warp(c_feat, h // 4, w // 4),
+        "flow_pyramid": pyr,
+        "gc_dual_prior_motion": 40 * n * c_mv * lh * lw,
+        "gc_dual_prior_frame": 40 * n * c_y * lh * lw,
+        "eb": 2 * 12 * n * c_z * zh * zw,
+    }
+    d["total"] = sum(d.values())
+    d["warp_multi"] = d["warp_x_ref"] + d["warp_ctx1"] + d["warp_ctx2"] + d["warp_ctx3"]
+    return d
+
+
+def synthetic_pframe_inputs(h, w, device, seed, n=1, regime="smooth", c_feat=64, c_mv=64,
+                            c_y=96, c_z=64):
+    """Synthetic tensors of SURVEY.md 8d config 2 (shapes of a random-init DMC
+    at H x W; values from the controlled distributions, not the degenerate
+    random-init activations).  Features are channels_last (the fast path)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def randn(*s):
+        return torch.randn(*s, device=device, generator=g)
+
+    cl = torch.channels_last
+    inp = {"x_ref": torch.rand(n, 3, h, w, device=device, generator=g)}
+    inp["feat1"] = randn(n, c_feat, h, w).contiguous(memory_format=cl)
+    inp["feat2"] = randn(n, c_feat, h // 2, w // 2).contiguous(memory_format=cl)
+    inp["feat3"] = randn(n, c_feat, h // 4, w // 4).contiguous(memory_format=cl)
+    if regime == "smooth":       # N(0,1) field, 31x31 box low-pass, sigma = 4 px
+        f = randn(n, 2, h, w)
+        f = torch.nn.functional.avg_pool2d(f, 31, stride=1, padding=15, count_include_pad=False)
+        inp["mv"] = (f / f.std() * 4.0).contiguous()
+    elif regime == "adversarial":  # i.i.d. N(0, 16^2) px
+        inp["mv"] = randn(n, 2, h, w) * 16.0
+    else:
+        raise ValueError(regime)
+    lh, lw, zh, zw = h // 16, w // 16, h // 64, w // 64
+
+    def latents(c):
+        mu = randn(n, c, lh, lw) * 3
+        sg = torch.exp(torch.empty(n, c, lh, lw, device=device).uniform_(
+            math.log(0.05), math.log(32), generator=g))
+        return mu, sg
+
+    for name, c in (("motion", c_mv), ("frame", c_y)):
+        mu, sg = latents(c)
+        inp[f"{name}.means"], inp[f"{name}.scales"] = mu, sg
+        inp[f"{name}.y"] = mu + sg * randn(n, c, lh, lw)
+        pm0, ps0 = latents(c // 2)
+        pm1, ps1 = latents(c // 2)
+        inp[f"{name}.prior"] = torch.cat((pm0, ps0, pm1, ps1), dim=1)   # chunk(4,1) layout
+        inp[f"{name}.z"] = randn(n, c_z, zh, zw) * 10
+    return inp
+
+
+class PFramePath:
+    """Binds one input set; ``launch()`` enqueues the whole P-frame hot path."""
+
+    LABELS = ("motion", "frame")
+
+    def __init__(self, inputs, eb_modules, gc_bounds=(0.11, 1e-9), num_pixels=None,
+                 materialize_pyramid=False):
+        self.inp = inputs
+        # mv2 / mv3 are only intermediates of DMC.motion_compensation
+        # (video_model.py:499-500); by default they are derived inside the warp
+        # kernel and never written to HBM
+        self.materialize_pyramid = materialize_pyramid
+        x_ref = inputs["x_ref"]
+        self.device = x_ref.device
+        n, _, h, w = x_ref.shape
+        self.n, self.h, self.w = n, h, w
+        self.num_pixels = float(num_pixels if num_pixels is not None else h * w)
+        L = nat.lib()
+        self._lib = L
+        dev = self.device
+        o = {}
+        o["mv2"] = torch.empty((n, 2, h // 2, w // 2), device=dev)
+        o["mv3"] = torch.empty((n, 2, h // 4, w // 4), device=dev)
+        o["warpframe"] = torch.empty_like(x_ref)
+        for k in (1, 2, 3):
+            o[f"context{k}"] = torch.empty_like(inputs[f"feat{k}"])
+        # [4 likelihood tensors][N] ln-sums: motion.y, motion.z, frame.y, frame.z (dict order
+        # of the reference's likelihood dicts, video_model.py:233, 577-579)
+        o["logsums"] = torch.zeros((4, n), dtype=torch.float64, device=dev)
+        o["bpp"] = torch.empty((4, n), dtype=torch.float32, device=dev)
+        o["bpp_total"] = torch.empty(n, dtype=torch.float32, device=dev)
+        o["bits"] = torch.empty(n, dtype=torch.float64, device=dev)
+        self._ws = [torch.zeros(L.dvc_rate_workspace_bytes(n), dtype=torch.uint8, device=dev)
+                    for _ in range(4)]
+        self._eb_params = {}
+        for li, name in enumerate(self.LABELS):
+            y = inputs[f"{name}.y"]
+            z = inputs[f"{name}.z"]
+            c = y.size(1)
+            o[f"{name}.params"] = torch.empty((n, 3 * c, y.size(2), y.size(3)), device=dev)
+            o[f"{name}.y_hat"] = torch.empty_like(y)
+            o[f"{name}.y_lik"] = torch.empty_like(y)
+            o[f"{name}.z_hat"] = torch.empty_like(z)
+            o[f"{name}.z_lik"] = torch.empty_like(z)
+            self._eb_params[name] = _packed_cached(eb_modules[name])
+        self.out = o
+        self._sb, self._lb = float(gc_bounds[0]), float(gc_bounds[1])
+        self._build_calls()
+
+    # -- argument lists are built once: launch() is a handful of foreign calls --
+    def _build_calls(self):
+        i, o, L = self.inp, self.out, self._lib
+        n, h, w = self.n, self.h, self.w
+        st, P = nat.st4, (lambda t: t.data_ptr())
+        self._keep = []
+
+        def keep(x):
+            self._keep.append(x)
+            return x
+
+        calls = []
+        mv = i["mv"]
+        if self.materialize_pyramid:
+            calls.append((L.dvc_flow_pyramid_fwd, "dvc_flow_pyramid_fwd",
+                          (P(mv), P(o["mv2"]), P(o["mv3"]), n, h, w, keep(st(mv)),
+                           keep(st(o["mv2"])), keep(st(o["mv3"])))))
+        tasks = (nat.WarpTask * 4)()
+        # largest task first; the pyramid levels are derived inside the kernel
+        for k, (im, level, out) in enumerate((
+                (i["feat1"], 0, o["context1"]), (i["feat2"], 1, o["context2"]),
+                (i["feat3"], 2, o["context3"]), (i["x_ref"], 0, o["warpframe"]))):
+            t = tasks[k]
+            t.im, t.flow, t.out = P(im), P(mv), P(out)
+            t.N, t.C, t.H, t.W = im.shape
+            t.im_st, t.flow_st, t.out_st = st(im), st(mv), st(out)
+            t.flow_downscale = level
+        keep(tasks)
+        self._warp_call = (L.dvc_warp_multi_fwd, "dvc_warp_multi_fwd",
+                           (ctypes.cast(tasks, ctypes.c_void_p), 4, 0))
+        ent = []
+        for li, name in enumerate(self.LABELS):
+            y, mu, sg = i[f"{name}.y"], i[f"{name}.means"], i[f"{name}.scales"]
+            prior, z = i[f"{name}.prior"], i[f"{name}.z"]
+            c, lh, lw = y.size(1), y.size(2), y.size(3)
+            mats, bias, fact, med = self._eb_params[name]
+            zl = o[f"{name}.z_lik"]
+            ls_y = o["logsums"][2 * li]
+            ls_z = o["logsums"][2 * li + 1]
+            ent.append((L.dvc_eb_likelihood_fwd, "dvc_eb_likelihood_fwd",
+                        (P(z), None, P(mats), P(bias), P(fact), P(med), None,
+                         P(o[f"{name}.z_hat"]), P(zl), P(ls_z), P(self._ws[2 * li + 1]),
+                         n, z.size(1), z.size(2), z.size(3), keep(st(z)), None, keep(st(zl)),
+                         self._lb)))
+            pr = o[f"{name}.params"]
+            ent.append((L.dvc_dual_prior_stage_a_fwd, "dvc_dual_prior_stage_a_fwd",
+                        (P(y), P(mu), P(sg), P(pr), n, c, lh, lw, keep(st(y)), keep(st(mu)),
+                         keep(st(sg)), keep(st(pr)))))
+            yh, yl = o[f"{name}.y_hat"], o[f"{name}.y_lik"]
+            ent.append((L.dvc_dual_prior_stage_b_gc_fwd, "dvc_dual_prior_stage_b_gc_fwd",
+                        (P(y), P(mu), P(sg), P(prior), None, P(yh), None, None, P(yl),
+                         None, None, None, None, P(ls_y), P(self._ws[2 * li]), n, c, lh, lw,
+                         keep(st(y)), keep(st(mu)), keep(st(sg)), keep(st(prior)), None,
+                         keep(st(yh)), None, self._sb, self._lb)))
+        ent.append((L.dvc_rate_finalize, "dvc_rate_finalize",
+                    (P(o["logsums"]), 4, n, self.num_pixels, P(o["bpp"]), P(o["bpp_total"]),
+                     P(o["bits"]))))
+        self._pre_calls = calls
+        self._ent_calls = ent
+
+    def launch(self, warp_events=None, concurrent=True):
+        """Enqueue the P-frame on the current stream of ``self.device``.
+
+        The motion-compensation branch (one launch) and the entropy branch (six
+        small launches + the rate finalise) are independent given the conv
+        outputs, so with ``concurrent=True`` the entropy branch goes to a
+        high-priority side stream, forked from and joined back into the current
+        stream with events: its latency-bound kernels then run inside the
+        bandwidth-bound warp instead of after it.  ``warp_events=(start, end)``
+        records two CUDA events around the dominant kernel (the multi-scale
+        warp) for the roofline measurement."""
+        main = torch.cuda.current_stream(self.device)
+        s = main.cuda_stream
+        side = None
+        if concurrent:
+            side = self._side_stream()
+            self._fork.record(main)
+            side.wait_event(self._fork)
+            s2 = side.cuda_stream
+            for fn, name, args in self._ent_calls:
+                rc = fn(*args, s2)
+                if rc:
+                    nat.check(rc, name)
+            self._join.record(side)
+        for fn, name, args in self._pre_calls:
+            rc = fn(*args, s)
+            if rc:
+                nat.check(rc, name)
+        if warp_events is not None:
+            warp_events[0].record(main)
+        fn, name, args = self._warp_call
+        rc = fn(*args, s)
+        if rc:
+            nat.check(rc, name)
+        if warp_events is not None:
+            warp_events[1].record(main)
+        if concurrent:
+            main.wait_event(self._join)
+        else:
+            for fn, name, args in self._ent_calls:
+                rc = fn(*args, s)
+                if rc:
+                    nat.check(rc, name)
+        return self.out
+
+    _side = {}
+
+    def _side_stream(self):
+        key = self.device.index
+        st = PFramePath._side.get(key)
+        if st is None:
+            st = torch.cuda.Stream(self.device, priority=-1)
+            PFramePath._side[key] = st
+        if not hasattr(self, "_fork"):
+            self._fork = torch.cuda.Event()
+            self._join = torch.cuda.Event()
+        return st
+
+    @property
+    def n_launches(self):
+        return len(self._pre_calls) + 1 + len(self._ent_calls)

@@ -98,15 +98,23 @@ int dvc_flow_pyramid_fwd(const float* mv, float* mv2, float* mv3, int64_t N,
 /* ---------------------------------------------------------------------------
  * Motion-compensation warps in one launch.  Replaces the non-conv part of
  * DMC.motion_compensation, dmc/models/video_model.py:497-504: warp x_ref by mv,
- * feat1 by mv, feat2 by mv2, feat3 by mv3.  mv2/mv3 come from
- * dvc_flow_pyramid_fwd.  All four problems are tiled into one grid.
+ * feat1 by mv, feat2 by mv2, feat3 by mv3.  mv2/mv3 either come from
+ * dvc_flow_pyramid_fwd or are derived inside the kernel (flow_downscale).  All
+ * four problems are tiled into one grid (largest first, so the small ones fill
+ * the tail).
  * ------------------------------------------------------------------------- */
 typedef struct dvc_warp_task {
   const float* im;
   const float* flow;
   float* out;
-  int64_t N, C, H, W;
+  int64_t N, C, H, W;            /* extents of im / out */
   int64_t im_st[4], flow_st[4], out_st[4];
+  /* 0: flow is [N,2,H,W].  k = 1, 2: flow is the full-resolution motion field
+   * [N,2,H<<k,W<<k]; the kernel reduces it on the fly with the reference's
+   * pyramid arithmetic (bilineardownsacling(.)/2 applied k times), so mv2/mv3
+   * never have to be written to HBM.  Bit-identical to warping with the
+   * materialised pyramid level. */
+  int64_t flow_downscale;
 } dvc_warp_task;
 int dvc_warp_multi_fwd(const dvc_warp_task* tasks /* HOST array */, int n_tasks,
                        int flags, dvc_stream_t stream);

@@ -69,7 +69,7 @@ def motion_compensation_warps(x_ref, feat1, feat2, feat3, mv):
     warpframe = flow_warp(x_ref, mv)
     mv2, mv3 = flow_pyramid(mv)
     return (flow_warp(feat1, mv), flow_warp(feat2, mv2), flow_warp(feat3, mv3),
-            warpframe, mv2, mv3)
+            warpframe)
 
 
 # --------------------------------------------------------------------------
@@ -176,3 +176,33 @@ def frame_bits(likelihoods):
         for p in fields.values():
             bits = bits + torch.log(p).sum(dim=(1, 2, 3)) / (-math.log(2))
     return bits
+
+
+# --------------------------------------------------------------------------
+# the timed region of one P-frame, reference ops only
+# --------------------------------------------------------------------------
+def pframe_hot_path(inp, eb_modules, gc, num_pixels=None):
+    """Reference-op restatement of the benchmark's timed region: the four
+    warps + flow pyramid of ``DMC.motion_compensation`` (video_model.py:497-504)
+    and, for both context models, the non-conv part of ``forward``
+    (video_model.py:218-233 / :390-406) with the spatial-prior conv replaced by
+    its precomputed output ``inp['<label>.prior']``; then the rate
+    (train.py:74-93).  ``inp`` uses the keys of
+    ``deepvideocodec_b200.pipeline.synthetic_pframe_inputs``."""
+    c1, c2, c3, wf = motion_compensation_warps(
+        inp["x_ref"], inp["feat1"], inp["feat2"], inp["feat3"], inp["mv"])
+    out = {"context1": c1, "context2": c2, "context3": c3, "warpframe": wf}
+    liks = {}
+    for label in ("motion", "frame"):
+        prior = inp[f"{label}.prior"]
+        y_hat, z_hat, lik = context_model_forward(
+            inp[f"{label}.y"], inp[f"{label}.z"], inp[f"{label}.means"], inp[f"{label}.scales"],
+            lambda params, _p=prior: _p, eb_modules[label], gc)
+        out[f"{label}.y_hat"], out[f"{label}.z_hat"] = y_hat, z_hat
+        out[f"{label}.y_lik"], out[f"{label}.z_lik"] = lik["y"], lik["z"]
+        liks[label] = lik
+    h, w = inp["x_ref"].shape[-2:]
+    npx = num_pixels if num_pixels is not None else h * w
+    out["bpp_total"], out["bpp_info"] = collect_likelihoods_list([liks], npx)
+    out["bits"] = frame_bits(liks)
+    return out

@@ -70,7 +70,11 @@ def test_flow_warp_properties_full_size(cuda_dev):
         memory_format=torch.channels_last)
     zero = torch.zeros(1, 2, 1088, 1920, device=cuda_dev)
     out = dvc.flow_warp(im, zero)
-    assert (out - im).abs().max().item() <= 2e-4 * im.abs().max().item()
+    from oracle import dmc_ref
+    assert torch.equal(out, dmc_ref.flow_warp(im, zero))
+    # identity only up to the reference's own fp32 coordinate noise (~1e-4 px at
+    # x~1900) times the white-noise image gradient
+    assert (out - im).abs().mean().item() <= 1e-3
     flow = zero.clone()
     flow[:, 0] = 5.0
     flow[:, 1] = -3.0
@@ -78,7 +82,8 @@ def test_flow_warp_properties_full_size(cuda_dev):
     ys = (torch.arange(1088, device=cuda_dev) - 3).clamp(0, 1087)
     xs = (torch.arange(1920, device=cuda_dev) + 5).clamp(0, 1919)
     expect = im[:, :, ys][:, :, :, xs]
-    assert (out - expect).abs().max().item() <= 1e-3
+    assert torch.equal(out, dmc_ref.flow_warp(im, flow))
+    assert (out - expect).abs().mean().item() <= 1e-3
     f2 = torch.randn(1, 2, 1088, 1920, device=cuda_dev, generator=g) * 3
     a = dvc.flow_warp(im, f2)
     b = dvc.flow_warp(im * 2.0, f2)
@@ -109,10 +114,13 @@ def test_flow_warp_golden_cpu_reference(cuda_dev, golden_dir):
         im = torch.from_numpy(z[f"{name}.im"]).to(cuda_dev)
         flow = torch.from_numpy(z[f"{name}.flow"]).to(cuda_dev)
         ref = torch.from_numpy(z[f"{name}.out"]).to(cuda_dev)
-        for ieee in (True, False):
+        # CPU eager divides the flow (ieee_div=True replays that: 1e-5 gate);
+        # the default replays CUDA eager's reciprocal multiply, one ulp of the
+        # source coordinate away from the CPU result -> looser bound.
+        for ieee, tol in ((True, WARP_ATOL), (False, 1e-4)):
             out = dvc.flow_warp(im, flow, ieee_div=ieee)
             err = (out - ref).abs().max().item()
-            assert err <= WARP_ATOL, (name, ieee, err)
+            assert err <= tol, (name, ieee, err)
         out = dvc.flow_warp(im.contiguous(memory_format=torch.channels_last), flow, ieee_div=True)
         assert (out - ref).abs().max().item() <= WARP_ATOL, name
 
@@ -163,8 +171,15 @@ def test_motion_compensation_warps_match(cuda_dev):
     mv = _smooth_flow(1, h, w, 4.0, cuda_dev, g)
     ref = dmc_ref.motion_compensation_warps(x_ref, f1, f2, f3, mv)
     out = dvc.motion_compensation_warps(x_ref, f1, f2, f3, mv)
+    assert len(out) == len(ref) == 4
     for o, r in zip(out, ref):
-        assert (o - r).abs().max().item() <= WARP_ATOL
+        assert torch.equal(o, r)          # one launch, pyramid evaluated in-kernel
+    # same thing through the materialised pyramid, NCHW features
+    mv2, mv3 = dvc.flow_pyramid(mv)
+    assert torch.equal(dvc.flow_warp(f2.contiguous(), mv2), ref[1])
+    assert torch.equal(dvc.flow_warp(f3.contiguous(), mv3), ref[2])
+    outs = dvc.warp_multi([(f2.contiguous(), mv, 1), (f3.contiguous(), mv, 2)])
+    assert torch.equal(outs[0], ref[1]) and torch.equal(outs[1], ref[2])
 
 
 def test_cpu_tensor_is_rejected(cuda_dev):
