@@ -76,7 +76,12 @@ _SIGNATURES = {
     "dvc_gc_likelihood_fwd": (
         c_int, [c_void_p] * 8 + [c_int64] * 4 + [_P4] * 5 + [c_float, c_float, c_void_p]),
     "dvc_gc_likelihood_bwd": (
-        c_int, [c_void_p] * 8 + [c_int64] * 4 + [_P4] + [c_float, c_float, c_void_p]),
+        c_int, [c_void_p] * 10 + [c_int64] * 4 + [_P4] * 7 + [c_float, c_float, c_void_p]),
+    "dvc_dual_prior_stage_a_bwd": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [_P4] * 2 + [c_void_p]),
+    "dvc_dual_prior_stage_b_gc_bwd": (
+        c_int, [c_void_p] * 14 + [c_int64] * 4 + [_P4] * 8 + [c_float, c_float, c_void_p]),
+    "dvc_eb_likelihood_bwd": (
+        c_int, [c_void_p] * 15 + [c_int64] * 4 + [_P4] * 4 + [c_float, c_void_p]),
     "dvc_eb_likelihood_fwd": (
         c_int, [c_void_p] * 11 + [c_int64] * 4 + [_P4] * 3 + [c_float, c_void_p]),
     "dvc_rate_finalize": (c_int, [c_void_p, c_int, c_int64, c_double] + [c_void_p] * 4),

@@ -280,7 +280,14 @@ def eb_forward(eb, z, training=None, want_outputs=True, want_zhat=False):
         if lb is None:
             lb = float(bound.bound.detach().cpu().reshape(-1)[0])
             eb._dvc_lik_bound = lb
-    noise = _launch_noise_like(z) if training else None
+    noise = None
+    if training:
+        # CompressAI draws the noise on its permuted [C, 1, N*H*W] view; drawing it
+        # in that layout and viewing it back as [N,C,H,W] (the kernel takes
+        # strides) consumes torch's generator exactly like the reference does
+        n_, c_, h_, w_ = z.shape
+        noise = torch.empty((c_, n_, h_, w_), dtype=z.dtype, device=z.device).uniform_(
+            -0.5, 0.5).permute(1, 0, 2, 3)
     params = [getattr(eb, f"_matrix{k}") for k in range(5)] + [eb.quantiles]
     needs_grad = torch.is_grad_enabled() and (
         z.requires_grad or any(p.requires_grad for p in params))

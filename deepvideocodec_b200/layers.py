@@ -119,7 +119,9 @@ class _Down2(torch.autograd.Function):
         grad_y = nat.require_cuda_f32(grad_y, "bilineardownsacling(grad)")
         n, c, h, w = ctx.shape
         fmt = torch.channels_last if ctx.channels_last else torch.contiguous_format
-        grad_x = torch.empty(ctx.shape, dtype=grad_y.dtype, device=grad_y.device, memory_format=fmt)
+        # odd sizes scatter with atomics into a zero-filled gradient
+        alloc = torch.empty if (h % 2 == 0 and w % 2 == 0) else torch.zeros
+        grad_x = alloc(ctx.shape, dtype=grad_y.dtype, device=grad_y.device, memory_format=fmt)
         with nat.device_of(grad_y):
             rc = nat.lib().dvc_bilinear_down2_bwd(grad_y.data_ptr(), grad_x.data_ptr(), n, c, h, w,
                                                   nat.st4(grad_y), nat.st4(grad_x), float(ctx.post),

@@ -78,7 +78,8 @@ int dvc_flow_warp_bwd(const float* grad_out, const float* im, const float* flow,
  * Flow pyramid.  Replaces bilineardownsacling(x) (layers.py:201-206) followed
  * by `* post_scale` (video_model.py:499-500 uses / 2 -> post_scale = 0.5).
  *   x [N,C,H,W] -> y [N,C,H/2,W/2];  any H,W >= 2 (odd sizes use the general
- *   align_corners=False formula).
+ *   align_corners=False formula; for odd sizes the backward scatters with
+ *   atomics and grad_x MUST be zero-filled by the caller).
  * ------------------------------------------------------------------------- */
 int dvc_bilinear_down2_fwd(const float* x, float* y, int64_t N, int64_t C,
                            int64_t H, int64_t W, const int64_t x_st[4],
@@ -182,17 +183,52 @@ int dvc_gc_likelihood_fwd(const float* inputs, const float* scales,
                           const int64_t noise_st[4], const int64_t out_st[4],
                           float scale_bound, float likelihood_bound,
                           dvc_stream_t stream);
-/* grad_lik [N,C,H,W] -> grad_inputs, grad_scales, grad_means (all [opt]).
+/* Backward of dvc_gc_likelihood_fwd (autograd of CompressAI
+ * GaussianConditional.forward as the reference's loss.backward() runs it,
+ * dmc/train.py:301).  Incoming: grad_lik [opt] [N,C,H,W], grad_logsum [opt]
+ * double[N] (gradient of the fused sum ln p), grad_out [opt] (gradient of
+ * `outputs`; only meaningful with noise).  Outgoing (all [opt], strides
+ * grad_st): grad_inputs, grad_scales, grad_means.
  * LowerBound rule: pass iff (x >= bound) or (grad < 0).  In eval mode the
- * rounding has zero gradient, so only grad_scales is non-zero through `lik`;
- * with noise the gradient flows to inputs and means as well. */
-int dvc_gc_likelihood_bwd(const float* grad_lik, const float* inputs,
+ * rounding has zero gradient, so only grad_scales is non-zero; with noise the
+ * gradient reaches inputs and means as well. */
+int dvc_gc_likelihood_bwd(const float* grad_lik, const double* grad_logsum,
+                          const float* grad_out, const float* inputs,
                           const float* scales, const float* means,
                           const float* noise, float* grad_inputs,
                           float* grad_scales, float* grad_means, int64_t N,
-                          int64_t C, int64_t H, int64_t W, const int64_t st[4],
+                          int64_t C, int64_t H, int64_t W, const int64_t in_st[4],
+                          const int64_t scales_st[4], const int64_t means_st[4],
+                          const int64_t noise_st[4], const int64_t glik_st[4],
+                          const int64_t gout_st[4], const int64_t grad_st[4],
                           float scale_bound, float likelihood_bound,
                           dvc_stream_t stream);
+
+/* Backward of dvc_dual_prior_stage_a_fwd: grad_params [N,3C,H,W] ->
+ * grad_y (= checkerboard-selected STE gradient), grad_means, grad_scales. */
+int dvc_dual_prior_stage_a_bwd(const float* grad_params, float* grad_y,
+                               float* grad_means, float* grad_scales, int64_t N,
+                               int64_t C, int64_t H, int64_t W,
+                               const int64_t gparams_st[4],
+                               const int64_t grad_st[4], dvc_stream_t stream);
+
+/* Backward of dvc_dual_prior_stage_b_gc_fwd.  Incoming (all [opt], strides
+ * gin_st): grad_y_hat, grad_means_hat, grad_scales_hat, grad_lik; grad_logsum
+ * [opt] double[N].  Outgoing (all [opt]): grad_y, grad_means, grad_scales
+ * (strides grad_st; zero where the spatial prior was selected) and grad_prior
+ * [N,2C,H,W] (zero where the first prior was selected). */
+int dvc_dual_prior_stage_b_gc_bwd(
+    const float* grad_y_hat, const float* grad_means_hat,
+    const float* grad_scales_hat, const float* grad_lik,
+    const double* grad_logsum, const float* y, const float* means,
+    const float* scales, const float* prior, const float* noise, float* grad_y,
+    float* grad_means, float* grad_scales, float* grad_prior, int64_t N,
+    int64_t C, int64_t H, int64_t W, const int64_t y_st[4],
+    const int64_t means_st[4], const int64_t scales_st[4],
+    const int64_t prior_st[4], const int64_t noise_st[4],
+    const int64_t gin_st[4], const int64_t grad_st[4],
+    const int64_t gprior_st[4], float scale_bound, float likelihood_bound,
+    dvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Factorised entropy bottleneck.  Replaces CompressAI EntropyBottleneck.forward
@@ -214,6 +250,24 @@ int dvc_eb_likelihood_fwd(const float* z, const float* noise,
                           int64_t H, int64_t W, const int64_t z_st[4],
                           const int64_t noise_st[4], const int64_t out_st[4],
                           float likelihood_bound, dvc_stream_t stream);
+
+/* Backward of dvc_eb_likelihood_fwd.  Incoming (all [opt], strides gin_st):
+ * grad_outputs, grad_z_hat, grad_lik; grad_logsum [opt] double[N].  Outgoing
+ * (all [opt]): grad_z (strides gz_st), grad_matrices[C*33], grad_biases[C*13],
+ * grad_factors[C*12] (w.r.t. the raw parameters, i.e. through softplus/tanh),
+ * grad_medians[C] (non-zero in eval mode only). */
+int dvc_eb_likelihood_bwd(const float* grad_outputs, const float* grad_z_hat,
+                          const float* grad_lik, const double* grad_logsum,
+                          const float* z, const float* noise,
+                          const float* matrices, const float* biases,
+                          const float* factors, const float* medians,
+                          float* grad_z, float* grad_matrices,
+                          float* grad_biases, float* grad_factors,
+                          float* grad_medians, int64_t N, int64_t C, int64_t H,
+                          int64_t W, const int64_t z_st[4],
+                          const int64_t noise_st[4], const int64_t gin_st[4],
+                          const int64_t gz_st[4], float likelihood_bound,
+                          dvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Piece 4: rate.  Replaces collect_likelihoods_list, dmc/train.py:74-93.

@@ -1,0 +1,180 @@
+"""CPU: host-side logic of the drop-in layer -- module surface, error
+behaviour without a GPU, patching of the reference, sharding and the scalar
+all-reduce (gloo, world_size 2), bench.py's reference arm."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_entropy_module_surface_matches_compressai_names():
+    import deepvideocodec_b200 as dvc
+    from test_oracle_golden import _oem
+    oem = _oem()
+    for ours, theirs in ((dvc.EntropyBottleneck(6), oem.EntropyBottleneck(6)),
+                         (dvc.GaussianConditional(None), oem.GaussianConditional(None))):
+        a, b = ours.state_dict(), theirs.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+        ours.load_state_dict(theirs.state_dict(), strict=True)
+    eb = dvc.EntropyBottleneck(6)
+    assert eb._get_medians().shape == (6, 1, 3 - 2)
+    assert [n for n, _ in eb.named_parameters() if n.endswith("quantiles")] == ["quantiles"]
+    assert torch.isfinite(eb.loss())
+    with pytest.raises(NotImplementedError):
+        dvc.EntropyBottleneck(4, filters=(3, 3))
+    for call in (lambda: eb.update(), lambda: eb.compress(None),
+                 lambda: dvc.GaussianConditional(None).build_indexes(None)):
+        with pytest.raises(NotImplementedError):
+            call()
+
+
+def test_aux_loss_matches_oracle():
+    import deepvideocodec_b200 as dvc
+    from test_oracle_golden import _oem
+    oem = _oem()
+    torch.manual_seed(3)
+    theirs = oem.EntropyBottleneck(5)
+    ours = dvc.EntropyBottleneck(5)
+    ours.load_state_dict(theirs.state_dict())
+    la, lb = ours.loss(), theirs.loss()
+    assert torch.equal(la, lb)
+    la.backward()
+    lb.backward()
+    assert torch.equal(ours.quantiles.grad, theirs.quantiles.grad)
+    assert ours._matrix0.grad is None          # parameters are detached in the aux loss
+
+
+def test_cpu_tensors_raise_no_fallback():
+    import deepvideocodec_b200 as dvc
+    x = torch.zeros(1, 4, 8, 8)
+    f = torch.zeros(1, 2, 8, 8)
+    calls = [
+        lambda: dvc.flow_warp(x, f),
+        lambda: dvc.bilineardownsacling(x),
+        lambda: dvc.flow_pyramid(f),
+        lambda: dvc.quantize_ste(x),
+        lambda: dvc.GaussianConditional(None)(x, x, x),
+        lambda: dvc.EntropyBottleneck(4)(x),
+        lambda: dvc.dual_prior_stage_a(x, x, x),
+        lambda: dvc.log_sum(x),
+        lambda: dvc.collect_likelihoods_list([{"motion": {"y": x}}], 64),
+    ]
+    for call in calls:
+        with pytest.raises(dvc.DvcError):
+            call()
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from deepvideocodec_b200 import _native as nat
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(nat.DvcError, match="no CPU or eager fallback"):
+        nat.lib()
+
+
+def test_algorithmic_bytes_match_survey():
+    from deepvideocodec_b200.pipeline import pframe_algorithmic_bytes
+    b = pframe_algorithmic_bytes(1088, 1920)
+    assert b["total"] == 1571681280                      # 1 571.68 MB, SURVEY.md 8d
+    assert b["warp_ctx1"] == 1086259200 and b["warp_x_ref"] == 66846720
+    assert b["flow_pyramid"] == 26112000
+    assert pframe_algorithmic_bytes(256, 256)["total"] == 49307648   # config 1: 49.31 MB
+
+
+def test_units_and_sharding():
+    from deepvideocodec_b200.dist import make_units, shard_units
+    units = make_units([96, 96, 50, 7])
+    assert [u.p_frames for u in units] == [31, 31, 31, 31, 31, 31, 31, 17, 6]
+    for world in (1, 2, 4, 8):
+        shards = [shard_units(units, r, world) for r in range(world)]
+        flat = sorted((u.sequence, u.start) for s in shards for u in s)
+        assert flat == sorted((u.sequence, u.start) for u in units)          # a partition
+        loads = [sum(u.p_frames for u in s) for s in shards]
+        assert max(loads) - min(loads) <= 31
+    with pytest.raises(ValueError):
+        shard_units(units, 2, 2)
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from deepvideocodec_b200.dist import RateStats, make_units, reduce_stats, shard_units
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    units = make_units([96, 96, 40])
+    mine = shard_units(units, rank, world)
+    frames = sum(u.p_frames for u in mine)
+    # deterministic fake per-frame bits so the reduced total is checkable
+    bits = float(sum(1000.0 * u.sequence + u.start for u in mine for _ in range(u.p_frames)))
+    red = reduce_stats(RateStats(bits=bits, sq_err=0.5 * frames, frames=frames,
+                                 pixels=frames * 1088.0 * 1920.0))
+    with open(os.path.join(out_dir, f"r{rank}.json"), "w") as f:
+        json.dump({"frames": red.frames, "bits": red.bits, "bpp": red.bpp, "local": frames}, f)
+    dist.destroy_process_group()
+
+
+def test_scalar_all_reduce_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    from deepvideocodec_b200.dist import make_units
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = [json.load(open(tmp_path / f"r{r}.json")) for r in range(2)]
+    units = make_units([96, 96, 40])
+    total_frames = sum(u.p_frames for u in units)
+    total_bits = float(sum(1000.0 * u.sequence + u.start for u in units for _ in range(u.p_frames)))
+    for r in res:
+        assert r["frames"] == total_frames and r["bits"] == total_bits    # sums identical on both ranks
+    assert res[0]["local"] + res[1]["local"] == total_frames
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/dmc"), reason="reference not present")
+def test_patch_rebinds_reference_names():
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import deepvideocodec_b200 as dvc
+assert dvc.install_compressai_shim() is True
+sys.path.insert(0, "/root/reference/dmc")
+import models
+vm = sys.modules["models.video_model"]; ly = sys.modules["models.layers"]
+torch.manual_seed(0)
+net = models.DMC()
+assert len(net.state_dict()) == 438
+assert type(net.motion_context_model.gaussian_conditional).__module__ == "deepvideocodec_b200.entropy_models"
+assert type(net.frame_context_model.entropy_bottleneck).__module__ == "deepvideocodec_b200.entropy_models"
+net.load_state_dict(net.state_dict())          # DMC.load_state_dict validates the buffer names
+stock = vm.flow_warp
+dvc.patch(models)
+assert vm.flow_warp is dvc.flow_warp and ly.flow_warp is dvc.flow_warp
+assert vm.quantize_ste is dvc.quantize_ste and vm.bilineardownsacling is dvc.bilineardownsacling
+assert vm.MotionContextModel.forward is dvc.motion_context_forward
+assert vm.FrameContextModel.forward_dual_prior is dvc.forward_dual_prior
+try:
+    net([torch.rand(1, 3, 64, 64), torch.rand(1, 3, 64, 64)])
+    raise SystemExit("expected DvcError on CPU tensors")
+except dvc.DvcError:
+    pass
+dvc.unpatch()
+assert vm.flow_warp is stock
+print("ok")
+''' % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_bench_reference_arm_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "P-frames/s"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["frame"] == [1088, 1920]
