@@ -120,8 +120,9 @@ class _Down2(torch.autograd.Function):
         n, c, h, w = ctx.shape
         fmt = torch.channels_last if ctx.channels_last else torch.contiguous_format
         # odd sizes scatter with atomics into a zero-filled gradient
-        alloc = torch.empty if (h % 2 == 0 and w % 2 == 0) else torch.zeros
-        grad_x = alloc(ctx.shape, dtype=grad_y.dtype, device=grad_y.device, memory_format=fmt)
+        grad_x = torch.empty(ctx.shape, dtype=grad_y.dtype, device=grad_y.device, memory_format=fmt)
+        if h % 2 or w % 2:
+            grad_x.zero_()
         with nat.device_of(grad_y):
             rc = nat.lib().dvc_bilinear_down2_bwd(grad_y.data_ptr(), grad_x.data_ptr(), n, c, h, w,
                                                   nat.st4(grad_y), nat.st4(grad_x), float(ctx.post),
