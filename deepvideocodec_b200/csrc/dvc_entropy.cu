@@ -24,39 +24,67 @@
 
 namespace dvc {
 
-constexpr int kEThreads = 256;
+constexpr int kEThreads = 128;  // 128 threads x <= 32 registers = 4096 registers: fits beside 6 resident warp CTAs
 
-struct Shape4 {
-  int N, C, H, W;
-  int c_fast;  // enumerate channel-fastest (channels_last) instead of w-fastest
-  int E;       // C*H*W
+// Per-sample iteration space, enumerated in the memory order of the lead tensor
+// so that consecutive threads touch consecutive addresses:
+//   mode 0 (NCHW)          a = c (grid.y), b = h*W + w
+//   mode 1 (channels_last) a = h (grid.y), b = w*C + c
+//   mode 2 / 3             a = 0, b = flat NCHW / NHWC index (any shape; real divisions)
+// The inner split b -> (h,w) or (w,c) is one multiply-high by a precomputed
+// reciprocal (exact while b*d < 2^32) instead of the ~40-instruction integer
+// division the first version spent per element (ncu: the element-wise kernels
+// were issue bound at 57% on index arithmetic).
+struct It {
+  int N, C, H, W, E;
+  int mode, A, B;
+  unsigned magic;   // ceil(2^32 / d), d = W (mode 0) or C (mode 1); 0 => divide
+  int chunks;       // CTAs along b (grid.x)
+  int per_block;    // ceil(B / chunks)
 };
+constexpr int kBatch = 2;  // elements per thread per trip: all loads first, then the math
 
-__device__ __forceinline__ void decode(const Shape4& s, int i, int& c, int& h, int& w) {
-  if (s.c_fast) {
-    c = i % s.C;
-    int r = i / s.C;
-    w = r % s.W;
-    h = r / s.W;
-  } else {
-    w = i % s.W;
-    int r = i / s.W;
+__device__ __forceinline__ void decode(const It& s, int a, int b, int& c, int& h, int& w) {
+  if (s.mode == 0) {
+    c = a;
+    h = s.magic ? (int)__umulhi((unsigned)b, s.magic) : b / s.W;
+    w = b - h * s.W;
+  } else if (s.mode == 1) {
+    h = a;
+    w = s.magic ? (int)__umulhi((unsigned)b, s.magic) : b / s.C;
+    c = b - w * s.C;
+  } else if (s.mode == 2) {
+    w = b % s.W;
+    int r = b / s.W;
     h = r % s.H;
     c = r / s.H;
+  } else {
+    c = b % s.C;
+    int r = b / s.C;
+    w = r % s.W;
+    h = r / s.W;
   }
 }
 
-struct TS {  // tensor + element strides
-  long long n, c, h, w;
+struct TS {  // element strides; (c,h,w) part of an offset always fits int32 (validated)
+  long long n;
+  int c, h, w;
 };
 static inline TS ts(const int64_t s[4]) {
   TS r;
-  if (s) { r.n = s[0]; r.c = s[1]; r.h = s[2]; r.w = s[3]; }
-  else { r.n = r.c = r.h = r.w = 0; }
+  if (s) { r.n = s[0]; r.c = (int)s[1]; r.h = (int)s[2]; r.w = (int)s[3]; }
+  else { r.n = 0; r.c = r.h = r.w = 0; }
   return r;
 }
+static inline bool ts_fits(const int64_t s[4], int64_t C, int64_t H, int64_t W) {
+  if (!s) return true;
+  long double m = 0;
+  const int64_t e[3] = {C - 1, H - 1, W - 1};
+  for (int i = 0; i < 3; ++i) m += (long double)(s[i + 1] < 0 ? -s[i + 1] : s[i + 1]) * e[i];
+  return m < 2147483647.0L;
+}
 __device__ __forceinline__ long long off(const TS& s, int n, int c, int h, int w) {
-  return n * s.n + c * s.c + h * s.h + w * s.w;
+  return n * s.n + (long long)(c * s.c + h * s.h + w * s.w);
 }
 
 // ---------------------------------------------------------------------------
@@ -127,15 +155,14 @@ static int rate_ws(RateWS& ws, void* workspace, double* logsum, int64_t N) {
   return DVC_OK;
 }
 
-static int blocks_per_sample(long long E, int per_thread) {
-  long long b = (E + (long long)kEThreads * per_thread - 1) / ((long long)kEThreads * per_thread);
-  if (b < 1) b = 1;
-  if (b > DVC_RATE_MAX_BLOCKS) b = DVC_RATE_MAX_BLOCKS;
-  return (int)b;
+static unsigned magic_for(long long extent_b, int d) {
+  // floor(b / d) == umulhi(b, ceil(2^32 / d)) for all b < extent_b iff extent_b * d < 2^32
+  if (d <= 1 || extent_b * (long long)d >= (1LL << 32)) return 0u;
+  return (unsigned)(((1ULL << 32) + (unsigned long long)d - 1ULL) / (unsigned long long)d);
 }
 
-static int make_shape(Shape4& s, int64_t N, int64_t C, int64_t H, int64_t W,
-                      const int64_t lead_st[4], const char* who) {
+static int make_it(It& s, int64_t N, int64_t C, int64_t H, int64_t W, const int64_t lead_st[4],
+                   int per_thread, const char* who) {
   if (!(N > 0 && C > 0 && H > 0 && W > 0))
     return fail(DVC_ERR_INVALID_ARGUMENT, "%s: empty tensor", who);
   if (N > 65535) return fail(DVC_ERR_INVALID_ARGUMENT, "%s: N > 65535", who);
@@ -143,9 +170,30 @@ static int make_shape(Shape4& s, int64_t N, int64_t C, int64_t H, int64_t W,
   if (E >= 2147483647LL) return fail(DVC_ERR_INVALID_ARGUMENT, "%s: C*H*W too large", who);
   s.N = (int)N; s.C = (int)C; s.H = (int)H; s.W = (int)W;
   s.E = (int)E;
-  s.c_fast = (lead_st && lead_st[1] == 1 && C > 1 && lead_st[3] != 1) ? 1 : 0;
+  const bool c_fast = lead_st && lead_st[1] == 1 && C > 1 && lead_st[3] != 1;
+  long long A, B;
+  int d;
+  if (!c_fast) { A = C; B = (long long)H * W; d = (int)W; s.mode = 0; }
+  else         { A = H; B = (long long)W * C; d = (int)C; s.mode = 1; }
+  if (A > DVC_RATE_MAX_BLOCKS || A > 65535) {   // odd shapes: flat enumeration
+    s.mode = c_fast ? 3 : 2;
+    A = 1; B = E; d = 1;
+  }
+  s.A = (int)A; s.B = (int)B;
+  s.magic = (s.mode <= 1) ? magic_for(B, d) : 0u;
+  long long chunks = (B + (long long)kEThreads * per_thread - 1) / ((long long)kEThreads * per_thread);
+  const long long cap = DVC_RATE_MAX_BLOCKS / A;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  s.chunks = (int)chunks;
+  s.per_block = (int)((B + chunks - 1) / chunks);
   return DVC_OK;
 }
+
+static dim3 grid_of(const It& s) { return dim3((unsigned)s.chunks, (unsigned)s.A, (unsigned)s.N); }
+
+#define DVC_REQUIRE_FITS(st, C_, who)                                                   \
+  DVC_REQUIRE(ts_fits(st, C_, H, W), "%s: tensor extent exceeds 2^31 elements per sample", who)
 
 // ---------------------------------------------------------------------------
 // Gaussian conditional core (CompressAI GaussianConditional._likelihood +
@@ -180,25 +228,36 @@ struct QuantP {
   const float* x;
   const float* offset;
   float* q;
-  Shape4 s;
+  It s;
   TS xs, qs;
   long long offset_st;
 };
 
+#define DVC_FOR_BATCH(s)                                                                   \
+  const int n = blockIdx.z, a = blockIdx.y;                                                \
+  const int b_begin = blockIdx.x * (s).per_block;                                          \
+  const int b_end = min((s).B, b_begin + (s).per_block);                                   \
+  for (int b0 = b_begin + threadIdx.x; b0 < b_end; b0 += kEThreads * kBatch)
+
 __global__ void __launch_bounds__(kEThreads) quantize_kernel(const QuantP p) {
-  const int n = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.s.E; i += gridDim.x * blockDim.x) {
-    int c, h, w;
-    decode(p.s, i, c, h, w);
-    const float x = __ldg(p.x + off(p.xs, n, c, h, w));
-    float q;
-    if (p.offset) {
-      const float m = __ldg(p.offset + c * p.offset_st);
-      q = add_rn(rintf(sub_rn(x, m)), m);
-    } else {
-      q = rintf(x);
+  DVC_FOR_BATCH(p.s) {
+    float x[kBatch], m[kBatch];
+    long long o[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int b = b0 + k * kEThreads;
+      if (b < b_end) {
+        int c, h, w;
+        decode(p.s, a, b, c, h, w);
+        x[k] = __ldg(p.x + off(p.xs, n, c, h, w));
+        m[k] = p.offset ? __ldg(p.offset + c * p.offset_st) : 0.f;
+        o[k] = off(p.qs, n, c, h, w);
+      }
     }
-    p.q[off(p.qs, n, c, h, w)] = q;
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)
+      if (b0 + k * kEThreads < b_end)
+        p.q[o[k]] = p.offset ? add_rn(rintf(sub_rn(x[k], m[k])), m[k]) : rintf(x[k]);
   }
 }
 
@@ -210,25 +269,39 @@ struct StageAP {
   const float* means;
   const float* scales;
   float* params;
-  Shape4 s;
+  It s;
   TS ys, ms, ss, ps;
 };
 
-__global__ void __launch_bounds__(kEThreads) stage_a_kernel(const StageAP p) {
-  const int n = blockIdx.y;
+__global__ void __launch_bounds__(kEThreads, 16) stage_a_kernel(const StageAP p) {
   const int half = p.s.C >> 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.s.E; i += gridDim.x * blockDim.x) {
-    int c, h, w;
-    decode(p.s, i, c, h, w);
-    const float y = __ldg(p.y + off(p.ys, n, c, h, w));
-    const float mu = __ldg(p.means + off(p.ms, n, c, h, w));
-    const float sg = __ldg(p.scales + off(p.ss, n, c, h, w));
-    // mask_0 = [(h+w) even] for the first channel half, mask_1 for the second
-    const bool sel = (((h + w) & 1) != 0) == (c >= half);
-    const float yh = sel ? dequantize(y, mu) : 0.0f;
-    p.params[off(p.ps, n, c, h, w)] = yh;
-    p.params[off(p.ps, n, p.s.C + c, h, w)] = mu;
-    p.params[off(p.ps, n, 2 * p.s.C + c, h, w)] = sg;
+  DVC_FOR_BATCH(p.s) {
+    float y[kBatch], mu[kBatch], sg[kBatch];
+    int po[kBatch];
+    bool sel[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int b = b0 + k * kEThreads;
+      if (b < b_end) {
+        int c, h, w;
+        decode(p.s, a, b, c, h, w);
+        y[k] = __ldg(p.y + off(p.ys, n, c, h, w));
+        mu[k] = __ldg(p.means + off(p.ms, n, c, h, w));
+        sg[k] = __ldg(p.scales + off(p.ss, n, c, h, w));
+        // mask_0 = [(h+w) even] for the first channel half, mask_1 for the second
+        sel[k] = (((h + w) & 1) != 0) == (c >= half);
+        po[k] = c * p.ps.c + h * p.ps.h + w * p.ps.w;
+      }
+    }
+    float* __restrict__ pp = p.params + n * p.ps.n;
+    const int cs = p.s.C * p.ps.c;
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)
+      if (b0 + k * kEThreads < b_end) {
+        pp[po[k]] = sel[k] ? dequantize(y[k], mu[k]) : 0.0f;
+        pp[po[k] + cs] = mu[k];
+        pp[po[k] + 2 * cs] = sg[k];
+      }
   }
 }
 
@@ -249,59 +322,70 @@ struct StageBP {
   float* q_w1;
   float* s_w0;
   float* s_w1;
-  Shape4 s;
+  It s;
   TS ys, ms, ss, prs, ns, os, hs;
   float scale_bound, lik_bound;
   int has_mean;
   RateWS ws;
 };
 
-__global__ void __launch_bounds__(kEThreads) stage_b_gc_kernel(const StageBP p) {
-  const int n = blockIdx.y;
+__global__ void __launch_bounds__(kEThreads, 16) stage_b_gc_kernel(const StageBP p) {
   const int half = p.s.C >> 1;
   float lsum = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.s.E; i += gridDim.x * blockDim.x) {
-    int c, h, w;
-    decode(p.s, i, c, h, w);
-    const float y = __ldg(p.y + off(p.ys, n, c, h, w));
-    float mu = 0.f, sg;
-    bool from_prior = true;
-    if (p.prior) {
-      const bool second = c >= half;
-      from_prior = (((h + w) & 1) != 0) == second;   // stage-A positions keep (means, scales)
-      if (from_prior) {
-        mu = __ldg(p.means + off(p.ms, n, c, h, w));
-        sg = __ldg(p.scales + off(p.ss, n, c, h, w));
-      } else {
-        // y_spatial_prior(params).chunk(4, 1) = (means_0, scales_0, means_1, scales_1)
-        const int cm = second ? (p.s.C + (c - half)) : c;
-        mu = __ldg(p.prior + off(p.prs, n, cm, h, w));
-        sg = __ldg(p.prior + off(p.prs, n, cm + half, h, w));
+  DVC_FOR_BATCH(p.s) {
+    float y[kBatch], mu[kBatch], sg[kBatch], nz[kBatch];
+    int oo[kBatch], oh[kBatch];
+    bool fp[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int b = b0 + k * kEThreads;
+      if (b < b_end) {
+        int c, h, w;
+        decode(p.s, a, b, c, h, w);
+        y[k] = __ldg(p.y + off(p.ys, n, c, h, w));
+        const float* pm = p.means + off(p.ms, n, c, h, w);
+        const float* psg = p.scales + off(p.ss, n, c, h, w);
+        fp[k] = true;
+        if (p.prior) {
+          const bool second = c >= half;
+          fp[k] = (((h + w) & 1) != 0) == second;   // stage-A positions keep (means, scales)
+          if (!fp[k]) {
+            // y_spatial_prior(params).chunk(4, 1) = (means_0, scales_0, means_1, scales_1)
+            const int cm = second ? (p.s.C + (c - half)) : c;
+            pm = p.prior + off(p.prs, n, cm, h, w);
+            psg = pm + (long long)half * p.prs.c;
+          }
+        }
+        mu[k] = p.has_mean ? __ldg(pm) : 0.f;
+        sg[k] = __ldg(psg);
+        nz[k] = p.noise ? __ldg(p.noise + off(p.ns, n, c, h, w)) : 0.f;
+        oo[k] = c * p.os.c + h * p.os.h + w * p.os.w;
+        oh[k] = ((c >= half) ? c - half : c) * p.hs.c + h * p.hs.h + w * p.hs.w;
       }
-    } else {
-      if (p.has_mean) mu = __ldg(p.means + off(p.ms, n, c, h, w));
-      sg = __ldg(p.scales + off(p.ss, n, c, h, w));
     }
-    // STE-rounded latent (always rounded, training or not: video_model.py:165-166)
-    const float q = rintf(p.has_mean ? sub_rn(y, mu) : y);
-    const float yh = p.has_mean ? add_rn(q, mu) : q;
-    // GaussianConditional.quantize: noise in training, dequantize in eval
-    const float outv = p.noise ? add_rn(y, __ldg(p.noise + off(p.ns, n, c, h, w))) : yh;
-    const float pr = gc_prob(outv, mu, p.has_mean != 0, sg, p.scale_bound, p.lik_bound);
-    const long long o = off(p.os, n, c, h, w);
-    if (p.y_hat) p.y_hat[o] = (p.prior || !p.noise) ? yh : outv;
-    if (p.means_hat) p.means_hat[o] = mu;
-    if (p.scales_hat) p.scales_hat[o] = sg;
-    if (p.lik) p.lik[o] = pr;
-    if (p.q_w0) {  // mode='compress' planes (video_model.py:209-214)
-      const int ch = (c >= half) ? c - half : c;
-      const long long oh = off(p.hs, n, ch, h, w);
-      if (from_prior) { p.q_w0[oh] = q; p.s_w0[oh] = sg; }
-      else            { p.q_w1[oh] = q; p.s_w1[oh] = sg; }
-    }
-    lsum += logf(pr);
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)
+      if (b0 + k * kEThreads < b_end) {
+        // STE-rounded latent (always rounded, training or not: video_model.py:165-166)
+        const float q = rintf(p.has_mean ? sub_rn(y[k], mu[k]) : y[k]);
+        const float yh = p.has_mean ? add_rn(q, mu[k]) : q;
+        // GaussianConditional.quantize: noise in training, dequantize in eval
+        const float outv = p.noise ? add_rn(y[k], nz[k]) : yh;
+        const float pr = gc_prob(outv, mu[k], p.has_mean != 0, sg[k], p.scale_bound, p.lik_bound);
+        const long long o = n * p.os.n + oo[k];
+        if (p.y_hat) p.y_hat[o] = (p.prior || !p.noise) ? yh : outv;
+        if (p.means_hat) p.means_hat[o] = mu[k];
+        if (p.scales_hat) p.scales_hat[o] = sg[k];
+        if (p.lik) p.lik[o] = pr;
+        if (p.q_w0) {  // mode='compress' planes (video_model.py:209-214)
+          const long long o2 = n * p.hs.n + oh[k];
+          if (fp[k]) { p.q_w0[o2] = q; p.s_w0[o2] = sg[k]; }
+          else       { p.q_w1[o2] = q; p.s_w1[o2] = sg[k]; }
+        }
+        lsum += logf(pr);
+      }
   }
-  rate_commit(p.ws, n, blockIdx.x, gridDim.x, lsum);
+  rate_commit(p.ws, blockIdx.z, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, lsum);
 }
 
 // ---------------------------------------------------------------------------
@@ -365,7 +449,7 @@ __device__ __forceinline__ float eb_logits(float t, const float* sp, const float
   return add_rn(acc, b[12]);
 }
 
-__global__ void __launch_bounds__(128) eb_kernel(const EBP p) {
+__global__ void __launch_bounds__(128, 16) eb_kernel(const EBP p) {
   __shared__ float sp[33], bb[13], tf[12];
   const int c = blockIdx.y, n = blockIdx.z;
   if (threadIdx.x < 33) sp[threadIdx.x] = softplus_t(__ldg(p.matrices + c * 33 + threadIdx.x));
@@ -399,19 +483,29 @@ __global__ void __launch_bounds__(128) eb_kernel(const EBP p) {
 // ---------------------------------------------------------------------------
 struct LogSumP {
   const float* lik;
-  Shape4 s;
+  It s;
   TS ls;
   RateWS ws;
 };
 __global__ void __launch_bounds__(kEThreads) log_sum_kernel(const LogSumP p) {
-  const int n = blockIdx.y;
   float lsum = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.s.E; i += gridDim.x * blockDim.x) {
-    int c, h, w;
-    decode(p.s, i, c, h, w);
-    lsum += logf(__ldg(p.lik + off(p.ls, n, c, h, w)));
+  DVC_FOR_BATCH(p.s) {
+    float v[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int b = b0 + k * kEThreads;
+      v[k] = 1.0f;
+      if (b < b_end) {
+        int c, h, w;
+        decode(p.s, a, b, c, h, w);
+        v[k] = __ldg(p.lik + off(p.ls, n, c, h, w));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)
+      if (b0 + k * kEThreads < b_end) lsum += logf(v[k]);
   }
-  rate_commit(p.ws, n, blockIdx.x, gridDim.x, lsum);
+  rate_commit(p.ws, blockIdx.z, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, lsum);
 }
 
 __global__ void rate_finalize_kernel(const double* __restrict__ logsums, int K, int N,
@@ -448,14 +542,15 @@ int dvc_quantize_fwd(const float* x, const float* offset, float* q, int64_t N, i
                      int64_t H, int64_t W, const int64_t x_st[4], int64_t offset_st,
                      const int64_t q_st[4], dvc_stream_t stream) {
   DVC_REQUIRE(x && q && x_st && q_st, "quantize: null pointer");
+  DVC_REQUIRE_FITS(x_st, C, "quantize");
+  DVC_REQUIRE_FITS(q_st, C, "quantize");
   QuantP p;
-  int rc = make_shape(p.s, N, C, H, W, x_st, "quantize");
+  int rc = make_it(p.s, N, C, H, W, x_st, kBatch, "quantize");
   if (rc) return rc;
   p.x = x; p.offset = offset; p.q = q;
   p.xs = ts(x_st); p.qs = ts(q_st);
   p.offset_st = offset_st;
-  dim3 grid(blocks_per_sample(p.s.E, 4), (unsigned)N);
-  quantize_kernel<<<grid, kEThreads, 0, (cudaStream_t)stream>>>(p);
+  quantize_kernel<<<grid_of(p.s), kEThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("quantize_kernel");
 }
 
@@ -470,13 +565,16 @@ int dvc_dual_prior_stage_a_fwd(const float* y, const float* means, const float* 
   DVC_REQUIRE((H % 2) == 0 && (W % 2) == 0,
               "dual_prior_stage_a: checkerboard needs even H and W (got %lld x %lld)",
               (long long)H, (long long)W);
+  DVC_REQUIRE_FITS(y_st, C, "dual_prior_stage_a");
+  DVC_REQUIRE_FITS(means_st, C, "dual_prior_stage_a");
+  DVC_REQUIRE_FITS(scales_st, C, "dual_prior_stage_a");
+  DVC_REQUIRE_FITS(params_st, 3 * C, "dual_prior_stage_a");
   StageAP p;
-  int rc = make_shape(p.s, N, C, H, W, y_st, "dual_prior_stage_a");
+  int rc = make_it(p.s, N, C, H, W, y_st, kBatch, "dual_prior_stage_a");
   if (rc) return rc;
   p.y = y; p.means = means; p.scales = scales; p.params = params;
   p.ys = ts(y_st); p.ms = ts(means_st); p.ss = ts(scales_st); p.ps = ts(params_st);
-  dim3 grid(blocks_per_sample(p.s.E, 2), (unsigned)N);
-  stage_a_kernel<<<grid, kEThreads, 0, (cudaStream_t)stream>>>(p);
+  stage_a_kernel<<<grid_of(p.s), kEThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("stage_a_kernel");
 }
 
@@ -484,8 +582,7 @@ static int launch_stage_b(StageBP& p, int64_t N, double* logsum, void* workspace
                           cudaStream_t stream, const char* who) {
   int rc = rate_ws(p.ws, workspace, logsum, N);
   if (rc) return rc;
-  dim3 grid(blocks_per_sample(p.s.E, 2), (unsigned)N);
-  stage_b_gc_kernel<<<grid, kEThreads, 0, stream>>>(p);
+  stage_b_gc_kernel<<<grid_of(p.s), kEThreads, 0, stream>>>(p);
   return check_launch(who);
 }
 
@@ -509,8 +606,15 @@ int dvc_dual_prior_stage_b_gc_fwd(
   const bool any_half = q_w0 || q_w1 || s_w0 || s_w1;
   DVC_REQUIRE(!any_half || (q_w0 && q_w1 && s_w0 && s_w1 && half_st),
               "dual_prior_stage_b_gc: compress planes must be given together");
+  DVC_REQUIRE_FITS(y_st, C, "dual_prior_stage_b_gc");
+  DVC_REQUIRE_FITS(means_st, C, "dual_prior_stage_b_gc");
+  DVC_REQUIRE_FITS(scales_st, C, "dual_prior_stage_b_gc");
+  DVC_REQUIRE_FITS(prior_st, 2 * C, "dual_prior_stage_b_gc");
+  DVC_REQUIRE_FITS(noise_st, C, "dual_prior_stage_b_gc");
+  DVC_REQUIRE_FITS(out_st, C, "dual_prior_stage_b_gc");
+  DVC_REQUIRE_FITS(half_st, C / 2, "dual_prior_stage_b_gc");
   StageBP p;
-  int rc = make_shape(p.s, N, C, H, W, y_st, "dual_prior_stage_b_gc");
+  int rc = make_it(p.s, N, C, H, W, y_st, kBatch, "dual_prior_stage_b_gc");
   if (rc) return rc;
   p.y = y; p.means = means; p.scales = scales; p.prior = prior; p.noise = noise;
   p.y_hat = y_hat; p.means_hat = means_hat; p.scales_hat = scales_hat; p.lik = lik;
@@ -533,8 +637,13 @@ int dvc_gc_likelihood_fwd(const float* inputs, const float* scales, const float*
   DVC_REQUIRE(!means || means_st, "gc_likelihood: means without strides");
   DVC_REQUIRE(!noise || noise_st, "gc_likelihood: noise without strides");
   DVC_REQUIRE(!(outputs || lik) || out_st, "gc_likelihood: outputs without strides");
+  DVC_REQUIRE_FITS(in_st, C, "gc_likelihood");
+  DVC_REQUIRE_FITS(scales_st, C, "gc_likelihood");
+  DVC_REQUIRE_FITS(means_st, C, "gc_likelihood");
+  DVC_REQUIRE_FITS(noise_st, C, "gc_likelihood");
+  DVC_REQUIRE_FITS(out_st, C, "gc_likelihood");
   StageBP p;
-  int rc = make_shape(p.s, N, C, H, W, in_st, "gc_likelihood");
+  int rc = make_it(p.s, N, C, H, W, in_st, kBatch, "gc_likelihood");
   if (rc) return rc;
   p.y = inputs; p.means = means; p.scales = scales; p.prior = nullptr; p.noise = noise;
   p.y_hat = outputs; p.means_hat = nullptr; p.scales_hat = nullptr; p.lik = lik;
@@ -581,15 +690,15 @@ int dvc_eb_likelihood_fwd(const float* z, const float* noise, const float* matri
 int dvc_log_sum_fwd(const float* lik, double* logsum, void* workspace, int64_t N, int64_t C,
                     int64_t H, int64_t W, const int64_t lik_st[4], dvc_stream_t stream) {
   DVC_REQUIRE(lik && logsum && lik_st, "log_sum: null pointer");
+  DVC_REQUIRE_FITS(lik_st, C, "log_sum");
   LogSumP p;
-  int rc = make_shape(p.s, N, C, H, W, lik_st, "log_sum");
+  int rc = make_it(p.s, N, C, H, W, lik_st, 2 * kBatch, "log_sum");
   if (rc) return rc;
   p.lik = lik;
   p.ls = ts(lik_st);
   rc = rate_ws(p.ws, workspace, logsum, N);
   if (rc) return rc;
-  dim3 grid(blocks_per_sample(p.s.E, 8), (unsigned)N);
-  log_sum_kernel<<<grid, kEThreads, 0, (cudaStream_t)stream>>>(p);
+  log_sum_kernel<<<grid_of(p.s), kEThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("log_sum_kernel");
 }
 

@@ -17,6 +17,8 @@
 //   * strided path (NCHW, C=3 frames, odd layouts): one thread per pixel,
 //     lanes along W (coalesced per channel plane), channel loop unrolled x4.
 // Source coordinates are computed once per pixel and reused for all channels.
+#include <stdlib.h>
+
 #include "dvc_common.cuh"
 
 namespace dvc {
@@ -114,6 +116,7 @@ struct WarpTask {
   int ppb;           // pixel columns per CTA tile
   int rows;          // rows per CTA tile
   int flow_level;    // 0: flow has im's resolution; k: flow is 2^k finer, reduced on the fly
+  int prefetch;      // vec4: 0 none, 1 south tap row if the flow is coherent (default), 2 both rows, 3 south always
   int tiles_x, tiles_y;
   int first_block, n_blocks;
 };
@@ -233,8 +236,33 @@ __device__ __forceinline__ void warp_tile_vec4(const WarpTask& t, int tile, TapS
     const float fy = fetch_flow(fl + t.fl_c, t.fl_h, t.fl_w, h, w, t.flow_level);
     const Taps T = make_taps(t.g, h, w, fx, fy);
     sm.wgt[threadIdx.x] = make_float4(T.nw, T.ne, T.sw, T.se);
-    sm.pos[threadIdx.x] = (int)((unsigned)(T.y0 * im_h4 + T.x0 * im_w4) |
-                                (T.dx ? kEastIn : 0u) | (T.dy ? kSouthIn : 0u));
+    const int o = T.y0 * im_h4 + T.x0 * im_w4;
+    sm.pos[threadIdx.x] = (int)((unsigned)o | (T.dx ? kEastIn : 0u) | (T.dy ? kSouthIn : 0u));
+    // Fire-and-forget L2 prefetch of this pixel's south tap row (west+east tap =
+    // one contiguous run of 2 pixels).  It costs no register and no scoreboard
+    // slot, so it deepens the DRAM queue beyond what the register file can hold
+    // as in-flight gathers; the demand loads of the tile's later rows (and, for a
+    // coherent flow, the north taps of the row below) then hit in L2.  For an
+    // incoherent flow (no tap shared between neighbouring pixels) the prefetch
+    // only doubles the L2 requests, so the warp votes: prefetch iff most pixels
+    // land within 2 px of where their upper neighbour's mapping predicts.
+    if (t.prefetch) {
+      const int up_o = __shfl_up_sync(0xffffffffu, o, 1);
+      const int dxy = o - up_o - im_h4;                 // 0 for a locally rigid flow
+      const bool coherent = (lane - pc * c4 == 0) || (abs(dxy) <= 2 * im_w4) ||
+                            (abs(dxy - im_h4) <= 2 * im_w4) || (abs(dxy + im_h4) <= 2 * im_w4);
+      const unsigned votes = __ballot_sync(0xffffffffu, coherent);
+      if (t.prefetch > 2 || __popc(votes) >= 24) {
+        const unsigned bytes = (unsigned)(c4 * 16) * (T.dx ? 2u : 1u);
+        const float4* base = reinterpret_cast<const float4*>(t.im + n * t.im_n) + o;
+        if (T.dy)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + im_h4), "r"(bytes)
+                       : "memory");
+        if (t.prefetch == 2)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes)
+                       : "memory");
+      }
+    }
   }
   __syncwarp();
 
@@ -252,24 +280,38 @@ __device__ __forceinline__ void warp_tile_vec4(const WarpTask& t, int tile, TapS
   const float4* __restrict__ wgt = sm.wgt + (wid << 5) + px * c4;
   const int* __restrict__ pos = sm.pos + (wid << 5) + px * c4;
 
+#ifndef DVC_WARP_RPI
+#define DVC_WARP_RPI 1   // rows (x4 gathers) in flight per lane; 1 row x 48 warps/SM measured best
+#endif
   int r = 0;
 #pragma unroll 1
-  for (; r + 2 <= rows; r += 2) {
-    const unsigned pa = (unsigned)pos[r], pb = (unsigned)pos[r + 1];
-    const float4 wa = wgt[r], wb = wgt[r + 1];
-    const bool all_in = ((pa & pb) >> 30) == 3u;
-    float4 a0, a1, a2, a3, b0, b1, b2, b3;
-    gather4(north, south, pa, im_w4, all_in, a0, a1, a2, a3);
-    gather4(north, south, pb, im_w4, all_in, b0, b1, b2, b3);
-    st_streaming(out4, blend4(a0, a1, a2, a3, wa));
-    st_streaming(out4 + out_h4, blend4(b0, b1, b2, b3, wb));
-    out4 += 2 * out_h4;
+  for (; r + DVC_WARP_RPI <= rows; r += DVC_WARP_RPI) {
+    unsigned ps[DVC_WARP_RPI];
+    float4 ws[DVC_WARP_RPI];
+    unsigned all = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < DVC_WARP_RPI; ++k) {
+      ps[k] = (unsigned)pos[r + k];
+      ws[k] = wgt[r + k];
+      all &= ps[k];
+    }
+    const bool all_in = (all >> 30) == 3u;
+    float4 v[DVC_WARP_RPI][4];
+#pragma unroll
+    for (int k = 0; k < DVC_WARP_RPI; ++k)
+      gather4(north, south, ps[k], im_w4, all_in, v[k][0], v[k][1], v[k][2], v[k][3]);
+#pragma unroll
+    for (int k = 0; k < DVC_WARP_RPI; ++k)
+      st_streaming(out4 + k * out_h4, blend4(v[k][0], v[k][1], v[k][2], v[k][3], ws[k]));
+    out4 += DVC_WARP_RPI * out_h4;
   }
-  if (r < rows) {
+#pragma unroll 1
+  for (; r < rows; ++r) {
     const unsigned pa = (unsigned)pos[r];
     float4 a0, a1, a2, a3;
     gather4(north, south, pa, im_w4, false, a0, a1, a2, a3);
     st_streaming(out4, blend4(a0, a1, a2, a3, wgt[r]));
+    out4 += out_h4;
   }
 }
 
@@ -312,7 +354,10 @@ __device__ __forceinline__ void warp_tile_strided(const WarpTask& t, int tile) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+#ifndef DVC_WARP_MINB
+#define DVC_WARP_MINB 6   // <= 40 registers -> 6 CTAs (48 warps) per SM
+#endif
+__global__ void __launch_bounds__(kThreads, DVC_WARP_MINB)
 warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
   int b = blockIdx.x;
   int k = 0;
@@ -356,6 +401,15 @@ static int build_task(WarpTask& t, const dvc_warp_task& in, int flags) {
   DVC_REQUIRE(in.flow_downscale >= 0 && in.flow_downscale <= 2,
               "flow_warp: flow_downscale must be 0, 1 or 2");
   t.flow_level = in.flow_downscale;
+  {
+    // tuning knob (not API): DVC_WARP_PREFETCH = 0 | 1 | 2
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("DVC_WARP_PREFETCH");
+      pf = e ? atoi(e) : 1;
+    }
+    t.prefetch = pf;
+  }
   DVC_REQUIRE(in.N > 0 && in.C > 0 && in.H > 0 && in.W > 0, "flow_warp: empty tensor");
   DVC_REQUIRE(in.H < (1 << 24) && in.W < (1 << 24) && in.N < 65536 && in.C < (1 << 24),
               "flow_warp: extent too large");

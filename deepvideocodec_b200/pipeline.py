@@ -252,7 +252,8 @@ class PFramePath:
         key = self.device.index
         st = PFramePath._side.get(key)
         if st is None:
-            st = torch.cuda.Stream(self.device, priority=-1)
+            import os
+            st = torch.cuda.Stream(self.device, priority=int(os.environ.get("DVC_SIDE_PRIORITY", "-1")))
             PFramePath._side[key] = st
         if not hasattr(self, "_fork"):
             self._fork = torch.cuda.Event()
