@@ -123,6 +123,10 @@ struct WarpTask {
 struct WarpBatch {
   WarpTask t[kMaxTasks];
   int n_tasks;
+  // block schedule: `interleaved` CTAs in cycles of `period`, then per-task tails
+  int interleaved, period;
+  int quota[kMaxTasks], qprefix[kMaxTasks];
+  int tail_first[kMaxTasks], tail_tile0[kMaxTasks];
 };
 
 // ---------------------------------------------------------------------------
@@ -359,13 +363,26 @@ __device__ __forceinline__ void warp_tile_strided(const WarpTask& t, int tile) {
 #endif
 __global__ void __launch_bounds__(kThreads, DVC_WARP_MINB)
 warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
-  int b = blockIdx.x;
-  int k = 0;
+  // block -> (task, tile).  The tasks are INTERLEAVED in proportion to their
+  // sizes (quota[k] CTAs of task k per cycle of `period` CTAs) instead of laid
+  // end to end: the 3-channel frame warp is L1-wavefront bound (scalar gathers)
+  // while the 64-channel warps are DRAM bound, so running them side by side
+  // overlaps the two limits; end to end the frame warp ran alone at the tail.
+  const int b = blockIdx.x;
+  int k = 0, tile;
+  if (b < batch.interleaved) {
+    const int cyc = b / batch.period, r = b - cyc * batch.period;
 #pragma unroll
-  for (int i = 1; i < kMaxTasks; ++i)
-    if (i < batch.n_tasks && b >= batch.t[i].first_block) k = i;
+    for (int i = 1; i < kMaxTasks; ++i)
+      if (i < batch.n_tasks && r >= batch.qprefix[i]) k = i;
+    tile = cyc * batch.quota[k] + (r - batch.qprefix[k]);
+  } else {
+#pragma unroll
+    for (int i = 1; i < kMaxTasks; ++i)
+      if (i < batch.n_tasks && b >= batch.tail_first[i]) k = i;
+    tile = batch.tail_tile0[k] + (b - batch.tail_first[k]);
+  }
   const WarpTask& t = batch.t[k];
-  const int tile = b - t.first_block;
   __shared__ TapSmem sm;
   if (t.mode == kModeVec4C64)
     warp_tile_vec4<16>(t, tile, sm);
@@ -465,6 +482,33 @@ static int launch_batch(const dvc_warp_task* tasks, int n_tasks, int flags,
   }
   for (int i = n_tasks; i < kMaxTasks; ++i) batch.t[i] = batch.t[0];
   DVC_REQUIRE(total < 2147483647LL, "warp_multi: grid too large");
+  // proportional interleave: quota[k] ~ n_blocks[k] * 32 / total (>= 1)
+  {
+    const int kPeriodTarget = 32;
+    int period = 0;
+    long long cycles = 1LL << 40;
+    for (int i = 0; i < kMaxTasks; ++i) {
+      int q = 0;
+      if (i < n_tasks) {
+        q = (int)((batch.t[i].n_blocks * (long long)kPeriodTarget + total / 2) / total);
+        if (q < 1) q = 1;
+        const long long c = batch.t[i].n_blocks / q;
+        if (c < cycles) cycles = c;
+      }
+      batch.quota[i] = q;
+      batch.qprefix[i] = period;
+      period += q;
+    }
+    if (n_tasks == 1) cycles = 0;   // nothing to interleave
+    batch.period = period;
+    batch.interleaved = (int)(cycles * period);
+    long long pos = batch.interleaved;
+    for (int i = 0; i < kMaxTasks; ++i) {
+      batch.tail_first[i] = (int)pos;
+      batch.tail_tile0[i] = (int)(cycles * batch.quota[i]);
+      if (i < n_tasks) pos += batch.t[i].n_blocks - cycles * batch.quota[i];
+    }
+  }
   warp_multi_kernel<<<(unsigned)total, kThreads, 0, stream>>>(batch);
   return check_launch("warp_multi_kernel");
 }

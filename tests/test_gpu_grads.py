@@ -229,3 +229,76 @@ def test_context_model_tail_backward(cuda_dev, training, fmt):
     assert ((res[1][1] - res[0][1]).abs() / res[0][1]).max().item() <= 1e-5
     for k, nm in ((2, "grad_y"), (3, "grad_means"), (4, "grad_scales"), (5, "grad_conv_weight")):
         _close(res[1][k], res[0][k], nm, 2e-4)
+
+
+class _MiniMotionContext(torch.nn.Module):
+    """Stand-in with the attribute names of the reference's MotionContextModel
+    (video_model.py:128-150) and small conv nets, so the *bound method* drop-in
+    `motion_context_forward` can be exercised end to end on the GPU box (the
+    reference itself cannot travel there)."""
+
+    def __init__(self, c, cz, eb_cls, gc_cls):
+        super().__init__()
+        nn = torch.nn
+        self.hyper_encoder = nn.Conv2d(c, cz, 3, stride=4, padding=1)
+        self.hyper_decoder = nn.ConvTranspose2d(cz, c, 4, stride=4)
+        self.y_prior_fusion = nn.Conv2d(2 * c, 2 * c, 3, padding=1)
+        self.y_spatial_prior = nn.Conv2d(3 * c, 2 * c, 3, padding=1)
+        self.entropy_bottleneck = eb_cls(cz)
+        self.gaussian_conditional = gc_cls(None)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_motion_context_model_drop_in(cuda_dev, training):
+    """`MotionContextModel.forward` (video_model.py:218-233) restated with oracle
+    ops vs the fused drop-in bound onto the same module: outputs, likelihoods,
+    bpp and every parameter gradient."""
+    import deepvideocodec_b200 as dvc
+    from oracle import dmc_ref
+    oem = _oracle_entropy_models()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    c, cz = 16, 8
+    torch.manual_seed(60)
+    ref = _MiniMotionContext(c, cz, oem.EntropyBottleneck, oem.GaussianConditional).to(cuda_dev)
+    mine = _MiniMotionContext(c, cz, dvc.EntropyBottleneck, dvc.GaussianConditional).to(cuda_dev)
+    mine.load_state_dict(ref.state_dict())
+    ref.train(training)
+    mine.train(training)
+    g = torch.Generator(device=cuda_dev).manual_seed(61)
+    y = torch.randn(2, c, 16, 16, device=cuda_dev, generator=g) * 3
+    y_ref = torch.randn(2, c, 16, 16, device=cuda_dev, generator=g)
+
+    def reference_forward(m, y, y_ref):          # video_model.py:218-233, op for op
+        z = m.hyper_encoder(y)
+        _, z_lik = m.entropy_bottleneck(z)
+        z_hat = dmc_ref.quantize_hyper(z, m.entropy_bottleneck._get_medians())
+        params = m.hyper_decoder(z_hat)
+        means, scales = m.y_prior_fusion(torch.cat((params, y_ref), dim=1)).chunk(2, 1)
+        y_hat, mh, sh = dmc_ref.dual_prior(y, means, scales, m.y_spatial_prior)
+        _, y_lik = m.gaussian_conditional(y, sh, mh)
+        return y_hat, {"y": y_lik, "z": z_lik}
+
+    out = []
+    for m, fwd, collect in ((ref, reference_forward, dmc_ref.collect_likelihoods_list),
+                            (mine, dvc.motion_context_forward, dvc.collect_likelihoods_list)):
+        m.zero_grad()
+        a = y.clone().requires_grad_(True)
+        torch.manual_seed(7)
+        y_hat, liks = fwd(m, a, y_ref)
+        bpp, info = collect([{"motion": liks}], 256 * 256)
+        loss = bpp.mean() + 1e-3 * (y_hat * y_hat).mean()
+        loss.backward()
+        out.append((y_hat.detach(), liks["y"].detach(), liks["z"].detach(), bpp.detach(), a.grad,
+                    {n: p.grad for n, p in m.named_parameters()}))
+    assert torch.equal(out[1][0], out[0][0])
+    for k in (1, 2):
+        assert ((out[1][k] - out[0][k]).abs() / out[0][k]).max().item() <= 5e-5
+    _close(out[1][3], out[0][3], "bpp")
+    _close(out[1][4], out[0][4], "grad_y", 5e-4)
+    for name, gref in out[0][5].items():
+        if gref is None:
+            assert out[1][5][name] is None or out[1][5][name].abs().max().item() == 0.0, name
+            continue
+        assert out[1][5][name] is not None, name
+        _close(out[1][5][name], gref, name, 1e-3)
