@@ -16,7 +16,8 @@ _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libdvc_b200.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(_REPO_DIR, "include")
-SOURCES = ("dvc_api.cu", "dvc_warp.cu", "dvc_warp_bwd.cu", "dvc_entropy.cu", "dvc_entropy_bwd.cu")
+SOURCES = ("dvc_api.cu", "dvc_warp.cu", "dvc_warp_bwd.cu", "dvc_entropy.cu", "dvc_entropy_bwd.cu",
+           "dvc_coder.cu")
 
 DVC_WARP_IEEE_DIV = 1
 DVC_RATE_MAX_BLOCKS = 1024
@@ -86,6 +87,20 @@ _SIGNATURES = {
         c_int, [c_void_p] * 11 + [c_int64] * 4 + [_P4] * 3 + [c_float, c_void_p]),
     "dvc_rate_finalize": (c_int, [c_void_p, c_int, c_int64, c_double] + [c_void_p] * 4),
     "dvc_log_sum_fwd": (c_int, [c_void_p] * 3 + [c_int64] * 4 + [_P4, c_void_p]),
+    "dvc_symbols_indexes_fwd": (
+        c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 2 + [c_int64] * 4 + [_P4] * 3 +
+        [c_float, c_void_p]),
+    "dvc_pmf_to_quantized_cdf": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "dvc_rans_scratch_bytes": (c_int64, [c_int64] * 3),
+    "dvc_rans_max_bytes": (c_int64, [c_int64] * 2),
+    "dvc_rans_encode": (
+        c_int, [c_void_p] * 6 + [c_int64, c_float] + [c_void_p] * 3 + [c_int64] * 2 +
+        [c_void_p, c_int64, c_void_p, c_void_p, c_void_p] + [c_int64] * 4 + [_P4] * 3 +
+        [c_int64, c_void_p]),
+    "dvc_rans_decode": (
+        c_int, [c_void_p, c_int64, c_void_p] + [c_void_p] * 3 + [c_int64, c_float] +
+        [c_void_p] * 3 + [c_int64] * 2 + [c_void_p] * 4 + [c_int64] * 4 + [_P4] * 3 +
+        [c_int64, c_void_p]),
 }
 
 

@@ -1,0 +1,261 @@
+"""Entropy-coder inputs and range-ANS bit streams on the GPU (SURVEY.md 8f rows
+f1 / f2) -- Python face of ``csrc/dvc_coder.cu``.
+
+These are the pieces of CompressAI the reference reaches only on its
+real-bitstream path (``dmc/test.py:187-188`` -> ``DMC.encode_inter`` /
+``decode_inter``): ``build_indexes``, ``quantize(.., "symbols")``,
+``compress`` and ``decompress`` of both entropy models
+(``dmc/models/video_model.py:238-283, 411-458``) and the CDF-table
+construction behind ``DMC.update`` (``:669-677``).
+
+A bit stream returned here is a ``bytes`` object per batch sample, like
+CompressAI's.  With ``stream_symbols > 0`` it is the ``DVC1`` container (many
+stock rans64 sub-streams, one GPU warp each -- see ``include/dvc_b200.h``);
+with ``stream_symbols == 0`` it is one raw stock stream, byte-compatible with
+CompressAI's ``RansEncoder.encode_with_indexes``.  The decoder tells the two
+apart from the first word.
+"""
+import os
+import struct
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+__all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "build_indexes", "quantize_symbols",
+           "pmf_to_quantized_cdf", "rans_encode", "rans_decode", "stream_symbols_of"]
+
+MAGIC = 0x31435644                     # "DVC1"
+DEFAULT_STREAM_SYMBOLS = int(os.environ.get("DVC_RANS_STREAM_SYMBOLS", "1024"))
+
+
+def _dev_i32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.int32:
+        raise nat.DvcError(f"{name}: expected a CUDA int32 tensor (run update() and move the "
+                           f"module to the GPU); there is no CPU coder in deepvideocodec_b200")
+    return t.contiguous()
+
+
+class Tables:
+    """Device views of a module's ``_quantized_cdf`` / ``_cdf_length`` / ``_offset``."""
+
+    def __init__(self, quantized_cdf, cdf_length, offset):
+        if quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if quantized_cdf.dim() != 2:
+            raise ValueError(f"Invalid CDF size {quantized_cdf.size()}")
+        if offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if offset.dim() != 1:
+            raise ValueError(f"Invalid offsets size {offset.size()}")
+        if cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if cdf_length.dim() != 1:
+            raise ValueError(f"Invalid offsets size {cdf_length.size()}")
+        self.cdf = _dev_i32(quantized_cdf, "_quantized_cdf")
+        self.size = _dev_i32(cdf_length, "_cdf_length")
+        self.offset = _dev_i32(offset, "_offset")
+        if self.size.numel() != self.cdf.size(0) or self.offset.numel() != self.cdf.size(0):
+            raise ValueError("CDF tables disagree on the number of distributions")
+
+
+def pmf_to_quantized_cdf(pmf, precision=16):
+    """CompressAI ``_CXX.pmf_to_quantized_cdf`` (host, setup time)."""
+    p = np.ascontiguousarray(np.asarray(pmf, dtype=np.float32).reshape(-1))
+    cdf = np.zeros(p.size + 1, dtype=np.int32)
+    rc = nat.lib().dvc_pmf_to_quantized_cdf(p.ctypes.data, p.size, int(precision), cdf.ctypes.data)
+    if rc != 0:
+        msg = nat.lib().dvc_last_error_string().decode()
+        raise ValueError(msg)
+    return cdf
+
+
+def _table_f32(scale_table, device):
+    if scale_table is None or scale_table.numel() == 0:
+        raise ValueError("Uninitialized scale table. Run update_scale_table() first")
+    t = scale_table.detach().to(device=device, dtype=torch.float32).contiguous()
+    if t.numel() > 256:
+        raise nat.DvcError("scale tables of more than 256 entries are not supported")
+    return t
+
+
+def build_indexes(scales, scale_table, scale_bound):
+    """``GaussianConditional.build_indexes``: int32 tensor shaped like ``scales``.
+    One launch instead of the reference's 63 compare-and-subtract passes."""
+    squeeze = None
+    if scales.dim() != 4:
+        squeeze = scales.shape
+        scales = scales.reshape(1, 1, 1, -1)
+    scales = nat.require_cuda_f32(scales, "build_indexes(scales)")
+    tab = _table_f32(scale_table, scales.device)
+    n, c, h, w = scales.shape
+    out = torch.empty((n, c, h, w), dtype=torch.int32, device=scales.device)
+    with nat.device_of(scales):
+        rc = nat.lib().dvc_symbols_indexes_fwd(
+            None, None, scales.data_ptr(), tab.data_ptr(), tab.numel(), None, out.data_ptr(),
+            n, c, h, w, None, None, nat.st4(scales), float(scale_bound), nat.stream_of(scales))
+    nat.check(rc, "dvc_symbols_indexes_fwd")
+    return out if squeeze is None else out.reshape(squeeze)
+
+
+def quantize_symbols(x, means=None):
+    """``EntropyModel.quantize(x, "symbols", means)``: ``int32(round(x - means))``."""
+    x = nat.require_cuda_f32(x, "quantize(inputs)")
+    if means is not None:
+        means = means.expand_as(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.int32, device=x.device)
+    with nat.device_of(x):
+        rc = nat.lib().dvc_symbols_indexes_fwd(
+            x.data_ptr(), nat.ptr(means), None, None, 0, out.data_ptr(), None, n, c, h, w,
+            nat.st4(x), nat.opt_st4(means), None, 0.0, nat.stream_of(x))
+    nat.check(rc, "dvc_symbols_indexes_fwd")
+    return out
+
+
+def _index_args(indexes, scales, scale_table, shape, device):
+    """(indexes_ptr, scales_ptr, table_ptr, T, scales_st, keepalive)."""
+    keep = []
+    if indexes is not None:
+        if tuple(indexes.shape) != tuple(shape):
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        idx = indexes
+        if not idx.is_cuda:
+            raise nat.DvcError("indexes must be a CUDA tensor; there is no CPU coder")
+        idx = idx.to(torch.int32).contiguous()
+        keep.append(idx)
+        return idx.data_ptr(), None, None, 0, None, keep
+    if scales is not None:
+        scales = nat.require_cuda_f32(scales, "scales")
+        if tuple(scales.shape) != tuple(shape):
+            raise ValueError("`scales` must have the shape of the coded tensor")
+        tab = _table_f32(scale_table, device)
+        keep += [scales, tab]
+        return None, scales.data_ptr(), tab.data_ptr(), tab.numel(), nat.st4(scales), keep
+    return None, None, None, 0, None, keep        # channel index (entropy bottleneck)
+
+
+_status = {}
+
+
+def _status_word(device):
+    t = _status.get(device.index)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _status[device.index] = t
+    return t
+
+
+def rans_encode(tables, x=None, means=None, symbols=None, indexes=None, scales=None,
+                scale_table=None, scale_bound=0.11, stream_symbols=None):
+    """Encode one tensor ``[N,C,H,W]`` -> ``list`` of ``N`` ``bytes``.
+
+    Symbols: ``symbols`` (int32) or ``round(x - means)``.  Table indexes:
+    ``indexes`` (int), or derived from ``scales`` like ``build_indexes``, or --
+    neither -- the channel number."""
+    if stream_symbols is None:
+        stream_symbols = DEFAULT_STREAM_SYMBOLS
+    src = x if x is not None else symbols
+    if src is None or (x is not None and symbols is not None):
+        raise ValueError("give exactly one of x / symbols")
+    if src.dim() != 4:
+        raise ValueError("expected a 4-D [N,C,H,W] tensor")
+    n, c, h, w = src.shape
+    dev = src.device
+    if x is not None:
+        x = nat.require_cuda_f32(x, "compress(inputs)")
+        if means is not None:
+            means = nat.require_cuda_f32(means, "compress(means)").expand_as(x)
+    else:
+        if not symbols.is_cuda:
+            raise nat.DvcError("symbols must be a CUDA tensor; there is no CPU coder")
+        symbols = symbols.to(torch.int32).contiguous()
+    ip, sp, tp, T, sst, keep = _index_args(indexes, scales, scale_table, src.shape, dev)
+    L = c * h * w
+    lib = nat.lib()
+    cap = lib.dvc_rans_max_bytes(L, int(stream_symbols))
+    scratch_bytes = lib.dvc_rans_scratch_bytes(n, L, int(stream_symbols))
+    if cap < 0 or scratch_bytes < 0:
+        raise nat.DvcError(f"rans_encode: unsupported partition (L={L}, S={stream_symbols})")
+    out = torch.empty((n, cap), dtype=torch.uint8, device=dev)
+    out_bytes = torch.empty(n, dtype=torch.int64, device=dev)
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+    status = _status_word(dev)
+    with nat.device_of(src):
+        rc = lib.dvc_rans_encode(
+            nat.ptr(x), nat.ptr(means), nat.ptr(symbols), ip, sp, tp, T, float(scale_bound),
+            tables.cdf.data_ptr(), tables.size.data_ptr(), tables.offset.data_ptr(),
+            tables.cdf.size(0), tables.cdf.size(1), out.data_ptr(), cap, out_bytes.data_ptr(),
+            scratch.data_ptr(), status.data_ptr(), n, c, h, w, nat.opt_st4(x),
+            nat.opt_st4(means), sst, int(stream_symbols), nat.stream_of(src))
+    nat.check(rc, "dvc_rans_encode")
+    sizes = torch.cat((out_bytes, status.to(torch.int64))).cpu().tolist()   # one D2H sync
+    if sizes[-1] != 0:
+        status.zero_()
+        raise ValueError("compress: an index lies outside the CDF tables")
+    strings = []
+    for i in range(n):
+        if sizes[i] < 0:
+            raise nat.DvcError(f"rans_encode: output capacity too small ({-sizes[i]} > {cap})")
+        strings.append(out[i, :sizes[i]].cpu().numpy().tobytes())
+    return strings
+
+
+def stream_symbols_of(string, n_symbols):
+    """Sub-stream length a bit stream was written with (0 = raw stock stream)."""
+    if len(string) >= 16 and len(string) % 4 == 0:
+        magic, L, S, ns = struct.unpack_from("<4I", string, 0)
+        if magic == MAGIC and L == n_symbols and S > 0 and ns == (L + S - 1) // S and \
+                len(string) >= 4 * (4 + ns):
+            return S
+    return 0
+
+
+def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=None,
+                scale_bound=0.11, means=None, device=None, want_symbols=False):
+    """Decode ``len(strings)`` bit streams into a ``[N,C,H,W]`` tensor
+    ``float(symbol) + means`` (``EntropyModel.dequantize``), or int32 symbols."""
+    if not isinstance(strings, (tuple, list)):
+        raise ValueError("Invalid `strings` parameter type.")
+    n, c, h, w = (int(v) for v in shape)
+    if len(strings) != n:
+        raise ValueError("Invalid strings or indexes parameters")
+    dev = tables.cdf.device if device is None else device
+    L = c * h * w
+    S = {stream_symbols_of(s, L) for s in strings}
+    if len(S) != 1:
+        raise ValueError("bit streams of one batch were written with different layouts")
+    S = S.pop()
+    for s in strings:
+        if len(s) < 8 or len(s) % 4:
+            raise ValueError("truncated bit stream")
+    stride = max(len(s) for s in strings)
+    host = np.zeros((n, stride), dtype=np.uint8)
+    for i, s in enumerate(strings):
+        host[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    buf = torch.from_numpy(host).to(dev, non_blocking=False)
+    in_bytes = torch.tensor([len(s) for s in strings], dtype=torch.int64, device=dev)
+    ip, sp, tp, T, sst, keep = _index_args(indexes, scales, scale_table, (n, c, h, w), dev)
+    if means is not None:
+        means = means.to(device=dev, dtype=torch.float32).expand(n, c, h, w)
+    out_f = out_s = None
+    if want_symbols:
+        out_s = torch.empty((n, c, h, w), dtype=torch.int32, device=dev)
+    else:
+        out_f = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
+    status = _status_word(dev)
+    with nat.device_of(buf):
+        rc = nat.lib().dvc_rans_decode(
+            buf.data_ptr(), stride, in_bytes.data_ptr(), ip, sp, tp, T, float(scale_bound),
+            tables.cdf.data_ptr(), tables.size.data_ptr(), tables.offset.data_ptr(),
+            tables.cdf.size(0), tables.cdf.size(1), nat.ptr(means), nat.ptr(out_f),
+            nat.ptr(out_s), status.data_ptr(), n, c, h, w, sst, nat.opt_st4(means),
+            nat.opt_st4(out_f), int(S), nat.stream_of(buf))
+    nat.check(rc, "dvc_rans_decode")
+    st = int(status.item())
+    if st != 0:
+        status.zero_()
+        raise ValueError("decompress: " + ("an index lies outside the CDF tables" if st == 1
+                                           else "malformed bit-stream container"))
+    return out_s if want_symbols else out_f

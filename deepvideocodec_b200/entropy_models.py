@@ -87,14 +87,77 @@ class EntropyModel(nn.Module):
             return q if means is None else q + means
         return q.int()
 
-    # real entropy coding: SURVEY.md section 8 rows f1/f2
-    def compress(self, *a, **k):
-        raise NotImplementedError("deepvideocodec_b200: bitstream coding is outside the hot path "
-                                  "(SURVEY.md 8f); estimated rate only")
+    # ---- real entropy coding: GPU rANS, csrc/dvc_coder.cu
+    @staticmethod
+    def dequantize(inputs, means=None, dtype=torch.float):
+        outputs = inputs.type_as(means) if means is not None else inputs.type(dtype)
+        return outputs if means is None else outputs + means
 
-    def decompress(self, *a, **k):
-        raise NotImplementedError("deepvideocodec_b200: bitstream coding is outside the hot path "
-                                  "(SURVEY.md 8f); estimated rate only")
+    def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
+        """Rows of ``pmf`` (+ their tail mass) -> int32 ``[n, max_length + 2]``
+        quantised CDFs (host, setup time: ``dvc_pmf_to_quantized_cdf``)."""
+        from . import coder
+        lengths = [int(v) for v in pmf_length.reshape(-1).tolist()]
+        rows = pmf.detach().to("cpu", torch.float32).numpy()
+        tails = tail_mass.detach().to("cpu", torch.float32).numpy().reshape(len(lengths), -1)
+        cdf = np.zeros((len(lengths), int(max_length) + 2), dtype=np.int32)
+        for i, n in enumerate(lengths):
+            q = coder.pmf_to_quantized_cdf(np.concatenate((rows[i, :n], tails[i, :1])),
+                                           self.entropy_coder_precision)
+            cdf[i, :q.size] = q
+        return torch.from_numpy(cdf).to(pmf.device)
+
+    def _tables(self):
+        from . import coder
+        return coder.Tables(self._quantized_cdf, self._cdf_length, self._offset)
+
+    def compress(self, inputs, indexes, means=None):
+        """``EntropyModel.compress``: one ``bytes`` per batch sample.  Symbols
+        (``round(inputs - means)``), table look-ups and the coder run on the GPU;
+        only the finished streams cross to the host."""
+        from . import coder
+        if inputs.dim() < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        tables = self._tables()
+        shape = inputs.shape
+        x, idx, mu = _as4d(inputs), _as4d(indexes), None
+        if means is not None:
+            mu = _as4d(means.expand(shape))
+        return coder.rans_encode(tables, x=x, means=mu, indexes=idx)
+
+    def decompress(self, strings, indexes, dtype=torch.float, means=None):
+        from . import coder
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if len(strings) != indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if indexes.dim() < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        tables = self._tables()
+        shape = indexes.shape
+        if means is not None:
+            if means.shape[:2] != shape[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.shape != shape and any(means.size(i) != 1 for i in range(2, len(shape))):
+                raise ValueError("Invalid means parameters")
+            means = _as4d(means.expand(shape))
+        idx = _as4d(indexes)
+        out = coder.rans_decode(strings, tables, idx.shape, indexes=idx, means=means,
+                                device=tables.cdf.device)
+        out = out.reshape(shape)
+        return out if dtype in (torch.float, None) or means is not None else out.type(dtype)
+
+
+def _as4d(t):
+    """View a ``[N, C, *spatial]`` tensor as ``[N, C, H, W]`` (the coder's
+    NCHW enumeration equals the flattened order for any number of spatial dims)."""
+    if t.dim() == 4:
+        return t
+    if t.dim() < 2:
+        raise ValueError("expected a tensor with at least 2 dimensions")
+    return t.reshape(t.size(0), t.size(1), 1, -1)
 
 
 # ---------------------------------------------------------------------------
@@ -160,13 +223,47 @@ class GaussianConditional(EntropyModel):
             torch.Tensor(tuple(float(s) for s in scale_table)) if scale_table else torch.Tensor())
         self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
 
+    @staticmethod
+    def _prepare_scale_table(scale_table):
+        return torch.Tensor(tuple(float(s) for s in scale_table))
+
+    @staticmethod
+    def _standardized_cumulative(inputs):
+        return 0.5 * torch.erfc(-(2 ** -0.5) * inputs)
+
+    @staticmethod
+    def _standardized_quantile(quantile):
+        import scipy.stats
+        return scipy.stats.norm.ppf(quantile)
+
     def update_scale_table(self, scale_table, force=False):
-        raise NotImplementedError("deepvideocodec_b200: CDF tables belong to the bitstream path "
-                                  "(SURVEY.md 8f)")
+        """CDF tables of the scale table (``DMC.update``, video_model.py:669-677).
+        Setup time, 64 rows: plain torch for the pmf, the library for the CDFs."""
+        if self._offset.numel() > 0 and not force:
+            return False
+        self.scale_table = self._prepare_scale_table(scale_table).to(self.scale_table.device)
+        self.update()
+        return True
+
+    def update(self):
+        reach = -self._standardized_quantile(self.tail_mass / 2)
+        centre = torch.ceil(self.scale_table * reach).int()
+        length = 2 * centre + 1
+        widest = int(length.max().item())
+        k = torch.arange(widest, device=centre.device).int()
+        dist = torch.abs(k - centre[:, None]).float()
+        sigma = self.scale_table.unsqueeze(1).float()
+        upper = self._standardized_cumulative((0.5 - dist) / sigma)
+        lower = self._standardized_cumulative((-0.5 - dist) / sigma)
+        self._quantized_cdf = self._pmf_to_cdf(upper - lower, 2 * lower[:, :1], length, widest)
+        self._offset = -centre
+        self._cdf_length = length + 2
 
     def build_indexes(self, scales):
-        raise NotImplementedError("deepvideocodec_b200: CDF tables belong to the bitstream path "
-                                  "(SURVEY.md 8f)")
+        """int32 table index per element -- one launch (``dvc_symbols_indexes_fwd``)
+        instead of the original's ``len(scale_table) - 1`` compare passes."""
+        from . import coder
+        return coder.build_indexes(scales, self.scale_table, self.lower_bound_scale.value())
 
     def forward(self, inputs, scales, means=None, training=None):
         if training is None:
@@ -341,22 +438,71 @@ class EntropyBottleneck(EntropyModel):
     def _get_medians(self):
         return self.quantiles[:, :, 1:2]
 
+    def _logits_cumulative(self, inputs, stop_gradient=True):
+        """Plain torch, used only on parameter-sized tensors (``loss``: the
+        ``[C,1,3]`` quantiles; ``update``: ``[C,1,<=~60]`` table samples)."""
+        import torch.nn.functional as F
+        pick = (lambda p: p.detach()) if stop_gradient else (lambda p: p)
+        logits = inputs
+        for k in range(5):
+            logits = torch.matmul(F.softplus(pick(getattr(self, f"_matrix{k}"))), logits)
+            logits = logits + pick(getattr(self, f"_bias{k}"))
+            if k < 4:
+                logits = logits + torch.tanh(pick(getattr(self, f"_factor{k}"))) * torch.tanh(logits)
+        return logits
+
     def update(self, force=False):
-        raise NotImplementedError("deepvideocodec_b200: CDF tables belong to the bitstream path "
-                                  "(SURVEY.md 8f)")
+        """Per-channel CDF tables from the learned quantiles (``DMC.update``,
+        video_model.py:669-677).  Setup time."""
+        if self._offset.numel() > 0 and not force:
+            return False
+        med = self.quantiles[:, 0, 1]
+        below = torch.clamp(torch.ceil(med - self.quantiles[:, 0, 0]).int(), min=0)
+        above = torch.clamp(torch.ceil(self.quantiles[:, 0, 2] - med).int(), min=0)
+        self._offset = -below
+        first = med - below
+        length = above + below + 1
+        widest = int(length.max().item())
+        samples = torch.arange(widest, device=first.device)[None, :] + first[:, None, None]
+        lower = self._logits_cumulative(samples - 0.5)
+        upper = self._logits_cumulative(samples + 0.5)
+        sign = -torch.sign(lower + upper)
+        pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+        tail = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+        self._quantized_cdf = self._pmf_to_cdf(pmf, tail, length, widest)
+        self._cdf_length = length + 2
+        return True
+
+    def _build_indexes(self, size):
+        shape = [1] * len(size)
+        shape[1] = -1
+        return torch.arange(size[1]).view(*shape).int().repeat(size[0], 1, *size[2:])
+
+    def compress(self, x):
+        """``EntropyBottleneck.compress(x)`` (video_model.py:238, :411): the table
+        index is the channel and the mean the channel median -- neither is
+        materialised; the kernel derives both."""
+        from . import coder
+        med = self._get_medians().detach().reshape(1, -1, 1, 1)
+        x4 = _as4d(x)
+        return coder.rans_encode(self._tables(), x=x4, means=med.expand(x4.shape))
+
+    def decompress(self, strings, size):
+        from . import coder
+        tables = self._tables()
+        shape = (len(strings), tables.cdf.size(0), *size)
+        med = self._get_medians().detach().reshape(1, -1, 1, 1)
+        n, c = shape[:2]
+        flat = (n, c, 1, int(np.prod(shape[2:]))) if len(shape) != 4 else shape
+        out = coder.rans_decode(strings, tables, flat, means=med.to(tables.cdf.device),
+                                device=tables.cdf.device)
+        return out.reshape(shape)
 
     def loss(self):
         """Auxiliary quantile loss (base_model.py:71-78, train.py:336).  It touches
         only the [C,1,3] quantiles and the (detached) per-channel parameters --
         3*C scalars, no data tensor -- so it is plain torch, not a kernel."""
-        import torch.nn.functional as F
-        logits = self.quantiles
-        for k in range(5):
-            logits = torch.matmul(F.softplus(getattr(self, f"_matrix{k}").detach()), logits)
-            logits = logits + getattr(self, f"_bias{k}").detach()
-            if k < 4:
-                logits = logits + torch.tanh(getattr(self, f"_factor{k}").detach()) * torch.tanh(logits)
-        return torch.abs(logits - self.target).sum()
+        return torch.abs(self._logits_cumulative(self.quantiles) - self.target).sum()
 
     def forward(self, x, training=None):
         outputs, _, lik = eb_forward(self, x, training=training, want_outputs=True)

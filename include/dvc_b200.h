@@ -286,6 +286,98 @@ int dvc_log_sum_fwd(const float* lik, double* logsum, void* workspace,
                     int64_t N, int64_t C, int64_t H, int64_t W,
                     const int64_t lik_st[4], dvc_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * SURVEY.md 8f row f1 (first "next" row): preparation of the real entropy
+ * coder's inputs.  Replaces, in one launch,
+ *   GaussianConditional.build_indexes(scales)  (CompressAI; call sites
+ *       video_model.py:248-249, 272, 282, 422-423, 447, 457):
+ *       s = max(scales, scale_bound); index = (T-1) - #{k < T-1 : s <= table[k]}
+ *       -- the reference does it in 63 compare-and-subtract passes;
+ *   EntropyModel.quantize(x, "symbols")        (CompressAI, used by compress):
+ *       symbol = int32(round(x [- means])).
+ *   scales [opt] [N,C,H,W] -> indexes [opt] int32 (contiguous NCHW order)
+ *   x      [opt] [N,C,H,W], means [opt]  -> symbols [opt] int32 (contiguous)
+ *   table: device float[T], ascending (exp(linspace(ln 0.11, ln 256, 64)),
+ *   base_model.py:43-49), T <= 256.
+ * ------------------------------------------------------------------------- */
+int dvc_symbols_indexes_fwd(const float* x, const float* means,
+                            const float* scales, const float* table, int64_t T,
+                            int32_t* symbols, int32_t* indexes, int64_t N,
+                            int64_t C, int64_t H, int64_t W,
+                            const int64_t x_st[4], const int64_t means_st[4],
+                            const int64_t scales_st[4], float scale_bound,
+                            dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * the bit streams.  Replaces CompressAI's CPU coder as the
+ * reference reaches it through
+ *   GaussianConditional.compress(inputs, indexes) / .decompress(strings, indexes)
+ *       (video_model.py:250-251, 273, 283, 424-425, 448, 458)
+ *   EntropyBottleneck.compress(x) / .decompress(strings, size)
+ *       (video_model.py:238-239, 257, 411-412, 431)
+ * i.e. EntropyModel.compress: symbols = int(round(x - means)); per sample
+ * RansEncoder.encode_with_indexes(symbols, indexes, cdf, cdf_length, offset)
+ * (rans64, 16-bit probabilities, 4-bit bypass nibbles), and the inverse.
+ *
+ * Layout of one sample's output (`stream_symbols` = S > 0): the L = C*H*W
+ * symbols in NCHW order are cut into ceil(L/S) sub-streams; each sub-stream is
+ * a complete stock rans64 stream over its slice; one warp encodes/decodes one
+ * sub-stream.  Container, little-endian u32 words:
+ *   'DVC1', L, S, n_streams, words[n_streams], sub-streams back to back.
+ * S = 0: ONE raw stock stream, no header -- byte-identical to CompressAI's
+ * RansEncoder.encode_with_indexes (interop mode; serial, slow).
+ *
+ * Symbols come from `symbols` (int32, contiguous [N][L]) or from `x` [N,C,H,W]
+ * (strided) minus `means` [opt] (strided; 0-strides broadcast, e.g. per-channel
+ * medians).  Table indexes come from `indexes` (int32, contiguous [N][L]), or
+ * are derived from `scales` (strided) exactly like build_indexes, or -- both
+ * NULL -- are the channel number (EntropyBottleneck._build_indexes).
+ * CDF tables are the module buffers: cdf int32[n_cdf][cdf_stride]
+ * (_quantized_cdf), cdf_size int32[n_cdf] (_cdf_length), offset int32[n_cdf]
+ * (_offset), all on the device.
+ *   out        device bytes, sample n at out + n*out_stride_bytes
+ *   out_bytes  device int64[N]: container size of each sample; NEGATIVE
+ *              (-needed) when out_stride_bytes was too small (nothing written)
+ *   scratch    dvc_rans_scratch_bytes(N, L, S) bytes
+ *   status     [opt] device int, set to 1 if an index fell outside [0, n_cdf)
+ * dvc_rans_max_bytes(L, S) is the worst-case container size of one sample.
+ * ------------------------------------------------------------------------- */
+/* HOST pointers (setup time, once per model): CompressAI's
+ * pmf_to_quantized_cdf as EntropyModel._pmf_to_cdf calls it from
+ * GaussianConditional.update_scale_table / EntropyBottleneck.update
+ * (video_model.py:669-677).  pmf float[n] -> cdf int32[n+1], cdf[0] = 0,
+ * cdf[n] = 2^precision, strictly increasing. */
+int dvc_pmf_to_quantized_cdf(const float* pmf, int64_t n, int precision,
+                             int32_t* cdf);
+int64_t dvc_rans_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols);
+int64_t dvc_rans_max_bytes(int64_t L, int64_t stream_symbols);
+int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
+                    const int32_t* indexes, const float* scales,
+                    const float* scale_table, int64_t T, float scale_bound,
+                    const int32_t* cdf, const int32_t* cdf_size,
+                    const int32_t* offset, int64_t n_cdf, int64_t cdf_stride,
+                    uint8_t* out, int64_t out_stride_bytes, int64_t* out_bytes,
+                    void* scratch, int* status, int64_t N, int64_t C, int64_t H,
+                    int64_t W, const int64_t x_st[4], const int64_t means_st[4],
+                    const int64_t scales_st[4], int64_t stream_symbols,
+                    dvc_stream_t stream);
+/* Inverse.  in: device bytes (sample n at in + n*in_stride_bytes, in_bytes
+ * device int64[N] = size of each container).  Writes out [opt] = float(symbol)
+ * + means [opt] (EntropyModel.dequantize; strided [N,C,H,W]) and/or
+ * out_symbols [opt] int32 contiguous.  status [opt]: 1 bad index, 2 malformed
+ * container (header/lengths inconsistent with L, S or in_bytes); a malformed
+ * container never reads out of bounds. */
+int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes,
+                    const int64_t* in_bytes, const int32_t* indexes,
+                    const float* scales, const float* scale_table, int64_t T,
+                    float scale_bound, const int32_t* cdf,
+                    const int32_t* cdf_size, const int32_t* offset,
+                    int64_t n_cdf, int64_t cdf_stride, const float* means,
+                    float* out, int32_t* out_symbols, int* status, int64_t N,
+                    int64_t C, int64_t H, int64_t W, const int64_t scales_st[4],
+                    const int64_t means_st[4], const int64_t out_st[4],
+                    int64_t stream_symbols, dvc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

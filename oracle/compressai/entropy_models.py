@@ -10,6 +10,12 @@ sites: ``dmc/models/video_model.py:150,220,222,232,322,392,394,405``,
 The op sequence is kept op-for-op (one torch op per arithmetic step, same
 constants, same association) because fp32 cancellation in ``upper - lower``
 makes 1e-5-relative likelihood parity order sensitive.
+
+Entropy-coding surface (``update``,
+``update_scale_table``, ``build_indexes``, ``compress``, ``decompress``; call
+sites ``video_model.py:238-283, 411-458, 669-677``): same published algorithm,
+with ``oracle/c/rans_ref.c`` in the role of CompressAI's C++ ``ans`` /
+``_CXX`` extensions.  Also unpinned (see that file's header).
 """
 import math
 
@@ -56,12 +62,96 @@ class EntropyModel(nn.Module):
             return outputs
         return outputs.int()
 
-    # entropy-coding surface: SURVEY.md section 8 rows f1/f2 (not on the hot path)
-    def compress(self, *a, **k):
-        raise NotImplementedError("oracle shim: real entropy coding is out of scope")
+    # ---- entropy-coding surface, restated from the
+    # published CompressAI EntropyModel; the coder itself is oracle/c/rans_ref.c
+    @staticmethod
+    def dequantize(inputs, means=None, dtype=torch.float):
+        if means is not None:
+            outputs = inputs.type_as(means)
+            outputs += means
+        else:
+            outputs = inputs.type(dtype)
+        return outputs
 
-    def decompress(self, *a, **k):
-        raise NotImplementedError("oracle shim: real entropy coding is out of scope")
+    def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
+        from .. import rans
+        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32,
+                          device=pmf.device)
+        for i, p in enumerate(pmf):
+            prob = torch.cat((p[: pmf_length[i]], tail_mass[i]), dim=0)
+            _cdf = torch.from_numpy(rans.pmf_to_quantized_cdf(
+                prob.detach().cpu().numpy(), self.entropy_coder_precision))
+            cdf[i, : _cdf.size(0)] = _cdf
+        return cdf
+
+    def _check_cdf_size(self):
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if len(self._quantized_cdf.size()) != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+
+    def _check_offsets_size(self):
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if len(self._offset.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._offset.size()}")
+
+    def _check_cdf_length(self):
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if len(self._cdf_length.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+
+    def compress(self, inputs, indexes, means=None):
+        from .. import rans
+        symbols = self.quantize(inputs, "symbols", means)
+        if len(inputs.size()) < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        strings = []
+        for i in range(symbols.size(0)):
+            rv = rans.encode_with_indexes(
+                symbols[i].reshape(-1).int().cpu().numpy(),
+                indexes[i].reshape(-1).int().cpu().numpy(),
+                self._quantized_cdf.cpu().numpy(),
+                self._cdf_length.reshape(-1).int().cpu().numpy(),
+                self._offset.reshape(-1).int().cpu().numpy())
+            strings.append(rv)
+        return strings
+
+    def decompress(self, strings, indexes, dtype=torch.float, means=None):
+        from .. import rans
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if len(indexes.size()) < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        if means is not None:
+            if means.size()[:2] != indexes.size()[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size():
+                for i in range(2, len(indexes.size())):
+                    if means.size(i) != 1:
+                        raise ValueError("Invalid means parameters")
+        cdf = self._quantized_cdf
+        outputs = cdf.new_empty(indexes.size())
+        for i, s in enumerate(strings):
+            values = rans.decode_with_indexes(
+                s, indexes[i].reshape(-1).int().cpu().numpy(), cdf.cpu().numpy(),
+                self._cdf_length.reshape(-1).int().cpu().numpy(),
+                self._offset.reshape(-1).int().cpu().numpy())
+            outputs[i] = torch.tensor(values, device=outputs.device,
+                                      dtype=outputs.dtype).reshape(outputs[i].size())
+        outputs = self.dequantize(outputs, means, dtype)
+        return outputs
 
 
 class EntropyBottleneck(EntropyModel):
@@ -98,7 +188,62 @@ class EntropyBottleneck(EntropyModel):
         return self.quantiles[:, :, 1:2]
 
     def update(self, force=False):
-        raise NotImplementedError("oracle shim: CDF tables are out of scope")
+        if self._offset.numel() > 0 and not force:
+            return False
+        medians = self.quantiles[:, 0, 1]
+        minima = medians - self.quantiles[:, 0, 0]
+        minima = torch.ceil(minima).int()
+        minima = torch.clamp(minima, min=0)
+        maxima = self.quantiles[:, 0, 2] - medians
+        maxima = torch.ceil(maxima).int()
+        maxima = torch.clamp(maxima, min=0)
+        self._offset = -minima
+        pmf_start = medians - minima
+        pmf_length = maxima + minima + 1
+        max_length = pmf_length.max().item()
+        device = pmf_start.device
+        samples = torch.arange(max_length, device=device)
+        samples = samples[None, :] + pmf_start[:, None, None]
+        half = float(0.5)
+        lower = self._logits_cumulative(samples - half, stop_gradient=True)
+        upper = self._logits_cumulative(samples + half, stop_gradient=True)
+        sign = -torch.sign(lower + upper)
+        pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+        pmf = pmf[:, 0, :]
+        tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+        quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._quantized_cdf = quantized_cdf
+        self._cdf_length = pmf_length + 2
+        return True
+
+    def _build_indexes(self, size):
+        dims = len(size)
+        N = size[0]
+        C = size[1]
+        view_dims = np.ones((dims,), dtype=np.int64)
+        view_dims[1] = -1
+        indexes = torch.arange(C).view(*view_dims)
+        indexes = indexes.int()
+        return indexes.repeat(N, 1, *size[2:])
+
+    @staticmethod
+    def _extend_ndims(tensor, n):
+        return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
+
+    def compress(self, x):
+        indexes = self._build_indexes(x.size())
+        medians = self._get_medians().detach()
+        spatial_dims = len(x.size()) - 2
+        medians = self._extend_ndims(medians, spatial_dims)
+        medians = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+        return super().compress(x, indexes, medians)
+
+    def decompress(self, strings, size):
+        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+        indexes = self._build_indexes(output_size).to(self._quantized_cdf.device)
+        medians = self._extend_ndims(self._get_medians().detach(), len(size))
+        medians = medians.expand(len(strings), *([-1] * (len(size) + 1)))
+        return super().decompress(strings, indexes, medians.dtype, medians)
 
     def loss(self):
         logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
@@ -172,11 +317,48 @@ class GaussianConditional(EntropyModel):
             "scale_bound",
             torch.Tensor([float(scale_bound)]) if scale_bound is not None else None)
 
+    @staticmethod
+    def _prepare_scale_table(scale_table):
+        return torch.Tensor(tuple(float(s) for s in scale_table))
+
+    @staticmethod
+    def _standardized_quantile(quantile):
+        import scipy.stats
+        return scipy.stats.norm.ppf(quantile)
+
     def update_scale_table(self, scale_table, force=False):
-        raise NotImplementedError("oracle shim: CDF tables are out of scope")
+        if self._offset.numel() > 0 and not force:
+            return False
+        device = self.scale_table.device
+        self.scale_table = self._prepare_scale_table(scale_table).to(device)
+        self.update()
+        return True
+
+    def update(self):
+        multiplier = -self._standardized_quantile(self.tail_mass / 2)
+        pmf_center = torch.ceil(self.scale_table * multiplier).int()
+        pmf_length = 2 * pmf_center + 1
+        max_length = torch.max(pmf_length).item()
+        device = pmf_center.device
+        samples = torch.abs(torch.arange(max_length, device=device).int() - pmf_center[:, None])
+        samples_scale = self.scale_table.unsqueeze(1)
+        samples = samples.float()
+        samples_scale = samples_scale.float()
+        upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
+        lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
+        pmf = upper - lower
+        tail_mass = 2 * lower[:, :1]
+        quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._quantized_cdf = quantized_cdf
+        self._offset = -pmf_center
+        self._cdf_length = pmf_length + 2
 
     def build_indexes(self, scales):
-        raise NotImplementedError("oracle shim: CDF tables are out of scope")
+        scales = self.lower_bound_scale(scales)
+        indexes = scales.new_full(scales.size(), len(self.scale_table) - 1).int()
+        for s in self.scale_table[:-1]:
+            indexes -= (scales <= s).int()
+        return indexes
 
     def _standardized_cumulative(self, inputs):
         half = float(0.5)

@@ -1,0 +1,320 @@
+"""GPU parity of the entropy-coder path through the C
+ABI (``dvc_symbols_indexes_fwd``, ``dvc_rans_encode``, ``dvc_rans_decode``):
+
+* bit streams are compared BYTE FOR BYTE with the plain-C oracle
+  (``oracle/c/rans_ref.c``): the raw mode (``stream_symbols = 0``) against one
+  stock stream, the ``DVC1`` container sub-stream by sub-stream against stock
+  streams of the corresponding slices;
+* decode(encode(x)) == round(x - means) + means, also at BASELINE.json's full
+  1080p latent sizes, where the coded size is additionally checked against the
+  estimated rate of the likelihood kernels (a size-independent property);
+* edge cases: one symbol, ragged last sub-stream, escapes (symbols outside the
+  table, both signs), bad indexes, malformed containers, strided inputs.
+"""
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _scale_table():
+    return np.exp(np.linspace(np.log(0.11), np.log(256), 64)).tolist()
+
+
+@pytest.fixture(scope="module")
+def gc_pair(cuda_dev):
+    """(oracle module on CPU, product module on the GPU) with identical tables."""
+    import deepvideocodec_b200 as dvc
+    from oracle.compressai import entropy_models as oem
+    o = oem.GaussianConditional(None)
+    o.update_scale_table(_scale_table())
+    p = dvc.GaussianConditional(None)
+    p.update_scale_table(_scale_table())
+    for name in ("_quantized_cdf", "_cdf_length", "_offset", "scale_table"):
+        assert torch.equal(getattr(o, name), getattr(p, name)), name
+    return o, p.to(cuda_dev).eval()
+
+
+@pytest.fixture(scope="module")
+def eb_pair(cuda_dev):
+    import deepvideocodec_b200 as dvc
+    from oracle.compressai import entropy_models as oem
+    torch.manual_seed(11)
+    o = oem.EntropyBottleneck(64)
+    torch.manual_seed(11)
+    p = dvc.EntropyBottleneck(64)
+    with torch.no_grad():
+        for m in (o, p):
+            m.quantiles[:, 0, 0] = -torch.linspace(3.2, 40, 64)
+            m.quantiles[:, 0, 2] = torch.linspace(1.5, 25, 64)
+            m.quantiles[:, 0, 1] = torch.linspace(-2, 2, 64)
+    o.update()
+    p.update()
+    for name in ("_quantized_cdf", "_cdf_length", "_offset"):
+        assert torch.equal(getattr(o, name), getattr(p, name)), name
+    return o, p.to(cuda_dev).eval()
+
+
+def _latents(shape, seed, dev, escapes=True):
+    g = torch.Generator().manual_seed(seed)
+    scales = torch.exp(torch.empty(shape).uniform_(np.log(0.05), np.log(64), generator=g))
+    means = torch.randn(shape, generator=g) * 3
+    y = means + scales * torch.randn(shape, generator=g)
+    if escapes:
+        flat = y.view(-1)
+        k = min(flat.numel(), 8)
+        flat[:k] += torch.tensor([4000.0, -4000.0, 70000.0, -70000.0, 1e6, -1e6, 300.0, -300.0])[:k]
+    return y.to(dev), means.to(dev), scales.to(dev)
+
+
+def _oracle_tables(o):
+    return (o._quantized_cdf.numpy(), o._cdf_length.numpy(), o._offset.numpy())
+
+
+def _split_container(s, L):
+    magic, n_sym, S, ns = struct.unpack_from("<4I", s, 0)
+    assert magic == 0x31435644 and n_sym == L and ns == (L + S - 1) // S
+    words = struct.unpack_from(f"<{ns}I", s, 16)
+    pos = 16 + 4 * ns
+    subs = []
+    for wds in words:
+        subs.append(s[pos:pos + 4 * wds])
+        pos += 4 * wds
+    assert pos == len(s)
+    return S, subs
+
+
+# ---------------------------------------------------------------------------
+# f1
+# ---------------------------------------------------------------------------
+def test_build_indexes_and_symbols_match_oracle(cuda_dev, gc_pair):
+    o, p = gc_pair
+    y, means, scales = _latents((2, 6, 10, 14), 1, cuda_dev)
+    scales.view(-1)[:64] = p.scale_table                    # exactly on a table entry
+    scales.view(-1)[64:127] = torch.nextafter(p.scale_table[:-1], p.scale_table[1:])
+    scales.view(-1)[200] = float("nan")
+    got = p.build_indexes(scales)
+    want = o.build_indexes(scales.cpu())
+    assert got.dtype == torch.int32 and torch.equal(got.cpu(), want)
+    # channels_last input: same values
+    got_cl = p.build_indexes(scales.contiguous(memory_format=torch.channels_last))
+    assert torch.equal(got_cl, got)
+    # non-4D input keeps its shape
+    assert torch.equal(p.build_indexes(scales.reshape(2, -1)).reshape(scales.shape), got)
+    sym = p.quantize(y, "symbols", means)
+    assert torch.equal(sym.cpu(), o.quantize(y.cpu(), "symbols", means.cpu()))
+    from deepvideocodec_b200 import coder
+    assert torch.equal(coder.quantize_symbols(y, means), sym)
+    assert torch.equal(coder.quantize_symbols(y), torch.round(y).int())
+
+
+# ---------------------------------------------------------------------------
+# f2: byte parity
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (1, 2, 2, 2), (2, 6, 10, 14), (1, 32, 68, 120)])
+def test_raw_mode_is_byte_identical_to_stock_stream(cuda_dev, gc_pair, shape):
+    from deepvideocodec_b200 import coder
+    from oracle import rans
+    o, p = gc_pair
+    y, means, scales = _latents(shape, 2, cuda_dev)
+    idx = p.build_indexes(scales)
+    strings = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=0)
+    sym = torch.round(y - means).int().cpu().numpy()
+    cdf, size, off = _oracle_tables(o)
+    for n in range(shape[0]):
+        want = rans.encode_with_indexes(sym[n], idx[n].cpu().numpy(), cdf, size, off)
+        assert strings[n] == want
+    # ... and the GPU decodes the oracle's stock stream
+    stock = [rans.encode_with_indexes(sym[n], idx[n].cpu().numpy(), cdf, size, off)
+             for n in range(shape[0])]
+    back = coder.rans_decode(stock, p._tables(), shape, indexes=idx, means=means)
+    assert torch.equal(back, torch.round(y - means) + means)
+    # the oracle decodes the GPU's stream
+    for n in range(shape[0]):
+        dec = rans.decode_with_indexes(strings[n], idx[n].cpu().numpy(), cdf, size, off)
+        assert np.array_equal(dec, sym[n])
+
+
+@pytest.mark.parametrize("shape,S", [((1, 2, 2, 2), 3), ((2, 6, 10, 14), 256), ((2, 6, 10, 14), 100),
+                                      ((1, 3, 5, 7), 1000), ((1, 32, 68, 120), 1024)])
+def test_container_substreams_are_stock_streams(cuda_dev, gc_pair, shape, S):
+    from deepvideocodec_b200 import coder
+    from oracle import rans
+    o, p = gc_pair
+    y, means, scales = _latents(shape, 3, cuda_dev)
+    L = shape[1] * shape[2] * shape[3]
+    # indexes derived from the scales inside the coder (fused build_indexes)
+    strings = coder.rans_encode(p._tables(), x=y, means=means, scales=scales,
+                                scale_table=p.scale_table, scale_bound=0.11, stream_symbols=S)
+    idx = o.build_indexes(scales.cpu()).numpy().reshape(shape[0], -1)
+    sym = torch.round(y - means).int().cpu().numpy().reshape(shape[0], -1)
+    cdf, size, off = _oracle_tables(o)
+    for n in range(shape[0]):
+        got_S, subs = _split_container(strings[n], L)
+        assert got_S == S and coder.stream_symbols_of(strings[n], L) == S
+        for j, sub in enumerate(subs):
+            sl = slice(j * S, min(L, (j + 1) * S))
+            assert sub == rans.encode_with_indexes(sym[n, sl], idx[n, sl], cdf, size, off), (n, j)
+    back = coder.rans_decode(strings, p._tables(), shape, scales=scales,
+                             scale_table=p.scale_table, scale_bound=0.11, means=means)
+    assert torch.equal(back, torch.round(y - means) + means)
+    syms = coder.rans_decode(strings, p._tables(), shape, indexes=torch.from_numpy(idx).to(
+        cuda_dev).reshape(shape), want_symbols=True)
+    assert torch.equal(syms.cpu().reshape(shape[0], -1), torch.from_numpy(sym))
+
+
+def test_module_compress_decompress_match_oracle_modules(cuda_dev, gc_pair, eb_pair, monkeypatch):
+    from deepvideocodec_b200 import coder
+    o, p = gc_pair
+    y, means, scales = _latents((2, 8, 12, 16), 4, cuda_dev)
+    idx = p.build_indexes(scales)
+    idx_cpu = o.build_indexes(scales.cpu())
+    want = o.compress(y.cpu(), idx_cpu, means.cpu())
+    monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", 0)
+    assert p.compress(y, idx, means) == want
+    # the reference's own call shape: compress(y_quant, indexes) without means
+    q = torch.round(y - means)
+    assert p.compress(q, idx) == o.compress(q.cpu(), idx_cpu)
+    assert torch.equal(p.decompress(want, idx, means=means).cpu(),
+                       o.decompress(want, idx_cpu, means=means.cpu()))
+    assert torch.equal(p.decompress(o.compress(q.cpu(), idx_cpu), idx).cpu(), q.cpu())
+    monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", 512)
+    s = p.compress(y, idx, means)
+    assert s != want and coder.stream_symbols_of(s[0], 8 * 12 * 16) == 512
+    assert torch.equal(p.decompress(s, idx, means=means), torch.round(y - means) + means)
+
+    eo, ep = eb_pair
+    z = (torch.randn(3, 64, 17, 30, generator=torch.Generator().manual_seed(5)) * 8).to(cuda_dev)
+    z[0, 0, 0, :2] += torch.tensor([500.0, -500.0], device=cuda_dev)
+    monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", 0)
+    zs = ep.compress(z)
+    assert zs == eo.compress(z.cpu())
+    zb = ep.decompress(zs, z.shape[-2:])
+    assert torch.equal(zb.cpu(), eo.decompress(zs, z.shape[-2:]))
+    med = ep._get_medians().detach().reshape(1, -1, 1, 1)
+    assert torch.equal(zb, torch.round(z - med) + med)
+    # z_hat of the coder == z_hat of the likelihood kernel (video_model.py:222-224 vs :239)
+    from deepvideocodec_b200.entropy_models import eb_forward
+    _, z_hat, _ = eb_forward(ep, z, want_outputs=False, want_zhat=True)
+    assert torch.equal(zb, z_hat)
+    monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", 1024)
+    assert torch.equal(ep.decompress(ep.compress(z), z.shape[-2:]), zb)
+
+
+def test_strided_inputs_and_broadcast_means(cuda_dev, gc_pair):
+    from deepvideocodec_b200 import coder
+    o, p = gc_pair
+    y, means, scales = _latents((2, 6, 10, 14), 6, cuda_dev, escapes=False)
+    idx = p.build_indexes(scales)
+    ref = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=128)
+    cl = torch.channels_last
+    got = coder.rans_encode(p._tables(), x=y.contiguous(memory_format=cl),
+                            means=means.contiguous(memory_format=cl),
+                            scales=scales.contiguous(memory_format=cl), scale_table=p.scale_table,
+                            stream_symbols=128)
+    assert got == ref
+    # per-channel broadcast mean (the entropy bottleneck's medians)
+    med = torch.linspace(-1, 1, 6, device=cuda_dev).reshape(1, 6, 1, 1)
+    a = coder.rans_encode(p._tables(), x=y, means=med.expand_as(y), indexes=idx, stream_symbols=128)
+    b = coder.rans_encode(p._tables(), x=y, means=med.expand_as(y).contiguous(), indexes=idx,
+                          stream_symbols=128)
+    assert a == b
+    out = coder.rans_decode(a, p._tables(), y.shape, indexes=idx, means=med)
+    assert torch.equal(out, torch.round(y - med) + med)
+
+
+def test_errors(cuda_dev, gc_pair):
+    import deepvideocodec_b200 as dvc
+    from deepvideocodec_b200 import coder
+    o, p = gc_pair
+    y, means, scales = _latents((1, 4, 6, 8), 7, cuda_dev)
+    idx = p.build_indexes(scales)
+    bad = idx.clone()
+    bad[0, 1, 2, 3] = 64
+    with pytest.raises(ValueError, match="outside the CDF tables"):
+        coder.rans_encode(p._tables(), x=y, means=means, indexes=bad)
+    # the status word is reset: the next call succeeds
+    s = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=64)
+    with pytest.raises(ValueError, match="outside the CDF tables"):
+        coder.rans_decode(s, p._tables(), y.shape, indexes=bad)
+    assert torch.equal(coder.rans_decode(s, p._tables(), y.shape, indexes=idx, means=means),
+                       torch.round(y - means) + means)
+    # malformed containers: a sub-stream length pointing past the end; wrong symbol count
+    w = bytearray(s[0])
+    struct.pack_into("<I", w, 16, 1 << 20)
+    with pytest.raises(ValueError, match="malformed"):
+        coder.rans_decode([bytes(w)], p._tables(), y.shape, indexes=idx)
+    with pytest.raises(ValueError):
+        coder.rans_decode([s[0][:6]], p._tables(), y.shape, indexes=idx)
+    with pytest.raises(ValueError):
+        coder.rans_decode(s + s, p._tables(), y.shape, indexes=idx)
+    with pytest.raises(ValueError, match="same size"):
+        p.compress(y, idx[:, :2])
+    with pytest.raises(dvc.DvcError):
+        p.compress(y.cpu(), idx.cpu())
+    # a truncated (but well-formed-looking) raw stream decodes zeros past its end, never faults
+    raw = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=0)
+    coder.rans_decode([raw[0][:8]], p._tables(), y.shape, indexes=idx)
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------
+# full 1080p latent sizes: round trip + coded size against the estimated rate
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("c", [64, 96])
+def test_full_size_round_trip_and_rate(cuda_dev, gc_pair, c):
+    from deepvideocodec_b200 import coder
+    o, p = gc_pair
+    shape = (1, c, 68, 120)
+    y, means, scales = _latents(shape, 8 + c, cuda_dev, escapes=False)
+    idx = p.build_indexes(scales)
+    _, lik = p(y, scales, means)
+    est_bits = float(-torch.log2(lik.double()).sum())
+    for S in (256, 1024, 4096):
+        s = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=S)
+        back = coder.rans_decode(s, p._tables(), shape, indexes=idx, means=means)
+        assert torch.equal(back, torch.round(y - means) + means)
+        n_streams = -(-c * 68 * 120 // S)
+        real_bits = 8 * len(s[0])
+        overhead = 32 * (4 + n_streams) + 48 * n_streams      # header + ~one state flush each
+        # 16-bit tables on a 64-entry scale grid: within a few percent of the estimate
+        assert abs(real_bits - overhead - est_bits) < 0.04 * est_bits + 20 * n_streams, \
+            (S, real_bits, est_bits)
+
+
+def test_reference_compress_call_sequence(cuda_dev, gc_pair):
+    """The sequence video_model.py:245-251 / :268-289 runs around the spatial
+    prior: compress planes of forward_dual_prior(mode='compress') -> two
+    strings -> decompress -> the same y_hat."""
+    from deepvideocodec_b200 import context
+    from oracle import dmc_ref
+    o, p = gc_pair
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(21)
+            self.y_spatial_prior = torch.nn.Conv2d(3 * 8, 2 * 8, 3, padding=1)
+            self.gaussian_conditional = p
+
+    m = Holder().to(cuda_dev).eval()
+    y, means, scales = _latents((1, 8, 12, 16), 22, cuda_dev, escapes=False)
+    with torch.no_grad():
+        y_hat, q0, q1, s0, s1 = context.forward_dual_prior(m, y, means, scales, mode="compress")
+        i0, i1 = p.build_indexes(s0), p.build_indexes(s1)
+        st0, st1 = p.compress(q0, i0), p.compress(q1, i1)
+        # decoder side, video_model.py:259-289
+        mask_0, mask_1 = dmc_ref.checkerboard_masks(12, 16, cuda_dev)
+        m0, m1 = means.chunk(2, 1)
+        sc0, sc1 = scales.chunk(2, 1)
+        r0 = p.decompress(st0, p.build_indexes(sc0 * mask_0 + sc1 * mask_1))
+        assert torch.equal(r0, q0)
+        y00, y11 = (r0 + m0) * mask_0, (r0 + m1) * mask_1
+        pm0, ps0, pm1, ps1 = m.y_spatial_prior(torch.cat((y00, y11, means, scales), 1)).chunk(4, 1)
+        r1 = p.decompress(st1, p.build_indexes(ps0 * mask_1 + ps1 * mask_0))
+        assert torch.equal(r1, q1)
+        y01, y10 = (r1 + pm0) * mask_1, (r1 + pm1) * mask_0
+        assert torch.equal(torch.cat((y00 + y01, y11 + y10), 1), y_hat)
