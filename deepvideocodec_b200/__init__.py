@@ -8,7 +8,10 @@ Importing the package never needs a GPU; calling an op needs the built
 """
 from ._native import DvcError, LIB_PATH, build_library, declared_symbols, lib  # noqa: F401
 from .context import (dual_prior_stage_a, dual_prior_stage_b_gc, forward_dual_prior,  # noqa: F401
-                      frame_context_forward, motion_context_forward)
+                      frame_context_compress, frame_context_decompress,
+                      frame_context_forward, motion_context_compress,
+                      motion_context_decompress, motion_context_forward)
+from . import coder  # noqa: F401
 from .entropy_models import (EntropyBottleneck, EntropyModel, GaussianConditional,  # noqa: F401
                              LowerBound)
 from .layers import (bilineardownsacling, flow_pyramid, flow_warp,  # noqa: F401

@@ -23,8 +23,9 @@ import torch
 
 from . import _native as nat
 
-__all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "build_indexes", "quantize_symbols",
-           "pmf_to_quantized_cdf", "rans_encode", "rans_decode", "stream_symbols_of"]
+__all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "build_indexes", "collect",
+           "decode_stage_a", "decode_stage_b", "pmf_to_quantized_cdf", "quantize_symbols",
+           "rans_decode", "rans_encode", "rans_encode_async", "stream_symbols_of"]
 
 MAGIC = 0x31435644                     # "DVC1"
 DEFAULT_STREAM_SYMBOLS = int(os.environ.get("DVC_RANS_STREAM_SYMBOLS", "1024"))
@@ -147,13 +148,24 @@ def _status_word(device):
     return t
 
 
-def rans_encode(tables, x=None, means=None, symbols=None, indexes=None, scales=None,
-                scale_table=None, scale_bound=0.11, stream_symbols=None):
-    """Encode one tensor ``[N,C,H,W]`` -> ``list`` of ``N`` ``bytes``.
+class PendingStreams:
+    """Bit streams of one ``rans_encode_async`` call, still on the device."""
+
+    def __init__(self, out, out_bytes, status, cap, keep):
+        self.out, self.out_bytes, self.status, self.cap, self._keep = out, out_bytes, status, cap, keep
+
+    def result(self):
+        return collect([self])[0]
+
+
+def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, scales=None,
+                      scale_table=None, scale_bound=0.11, stream_symbols=None):
+    """Launch the encoder for one tensor ``[N,C,H,W]``; no host synchronisation.
 
     Symbols: ``symbols`` (int32) or ``round(x - means)``.  Table indexes:
     ``indexes`` (int), or derived from ``scales`` like ``build_indexes``, or --
-    neither -- the channel number."""
+    neither -- the channel number.  ``collect`` turns pending results into
+    ``bytes`` with a single device->host round trip for any number of them."""
     if stream_symbols is None:
         stream_symbols = DEFAULT_STREAM_SYMBOLS
     src = x if x is not None else symbols
@@ -190,16 +202,43 @@ def rans_encode(tables, x=None, means=None, symbols=None, indexes=None, scales=N
             scratch.data_ptr(), status.data_ptr(), n, c, h, w, nat.opt_st4(x),
             nat.opt_st4(means), sst, int(stream_symbols), nat.stream_of(src))
     nat.check(rc, "dvc_rans_encode")
-    sizes = torch.cat((out_bytes, status.to(torch.int64))).cpu().tolist()   # one D2H sync
+    return PendingStreams(out, out_bytes, status, cap, keep + [x, means, symbols, scratch])
+
+
+def collect(pendings):
+    """``[PendingStreams] -> [[bytes per sample]]``: one D2H read of all sizes,
+    one D2H copy of all payload bytes."""
+    if not pendings:
+        return []
+    status = pendings[0].status
+    sizes = torch.cat([p.out_bytes for p in pendings] + [status.to(torch.int64)]).cpu().tolist()
     if sizes[-1] != 0:
         status.zero_()
         raise ValueError("compress: an index lies outside the CDF tables")
-    strings = []
-    for i in range(n):
-        if sizes[i] < 0:
-            raise nat.DvcError(f"rans_encode: output capacity too small ({-sizes[i]} > {cap})")
-        strings.append(out[i, :sizes[i]].cpu().numpy().tobytes())
+    pieces, k = [], 0
+    for p in pendings:
+        for i in range(p.out.size(0)):
+            if sizes[k] < 0:
+                raise nat.DvcError(f"rans_encode: output capacity too small "
+                                   f"({-sizes[k]} > {p.cap})")
+            pieces.append(p.out[i, :sizes[k]])
+            k += 1
+    blob = (torch.cat(pieces) if len(pieces) > 1 else pieces[0]).cpu().numpy().tobytes()
+    strings, k, pos = [], 0, 0
+    for p in pendings:
+        row = []
+        for _ in range(p.out.size(0)):
+            row.append(blob[pos:pos + sizes[k]])
+            pos += sizes[k]
+            k += 1
+        strings.append(row)
     return strings
+
+
+def rans_encode(tables, **kwargs):
+    """Encode one tensor ``[N,C,H,W]`` -> ``list`` of ``N`` ``bytes``
+    (``rans_encode_async`` + ``collect``)."""
+    return rans_encode_async(tables, **kwargs).result()
 
 
 def stream_symbols_of(string, n_symbols):
@@ -213,9 +252,11 @@ def stream_symbols_of(string, n_symbols):
 
 
 def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=None,
-                scale_bound=0.11, means=None, device=None, want_symbols=False):
+                scale_bound=0.11, means=None, device=None, want_symbols=False, cb=None):
     """Decode ``len(strings)`` bit streams into a ``[N,C,H,W]`` tensor
-    ``float(symbol) + means`` (``EntropyModel.dequantize``), or int32 symbols."""
+    ``float(symbol) + means`` (``EntropyModel.dequantize``), or int32 symbols.
+    ``cb = (parity, alt_elements)``: checkerboard pairing of ``scales`` (see
+    ``dvc_rans_decode`` in include/dvc_b200.h)."""
     if not isinstance(strings, (tuple, list)):
         raise ValueError("Invalid `strings` parameter type.")
     n, c, h, w = (int(v) for v in shape)
@@ -251,7 +292,8 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
             tables.cdf.data_ptr(), tables.size.data_ptr(), tables.offset.data_ptr(),
             tables.cdf.size(0), tables.cdf.size(1), nat.ptr(means), nat.ptr(out_f),
             nat.ptr(out_s), status.data_ptr(), n, c, h, w, sst, nat.opt_st4(means),
-            nat.opt_st4(out_f), int(S), nat.stream_of(buf))
+            nat.opt_st4(out_f), int(S), -1 if cb is None else int(cb[0]),
+            0 if cb is None else int(cb[1]), nat.stream_of(buf))
     nat.check(rc, "dvc_rans_decode")
     st = int(status.item())
     if st != 0:
@@ -259,3 +301,40 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
         raise ValueError("decompress: " + ("an index lies outside the CDF tables" if st == 1
                                            else "malformed bit-stream container"))
     return out_s if want_symbols else out_f
+
+
+def decode_stage_a(q0, means, scales):
+    """``params = cat((q0 + means_0) * mask_0, (q0 + means_1) * mask_1, means,
+    scales)`` (video_model.py:274-277 == :449-452): the spatial-prior conv input
+    on the decoder side.  ``q0``: int32 symbols ``[N, C/2, H, W]``."""
+    means = nat.require_cuda_f32(means, "decode_stage_a(means)")
+    scales = nat.require_cuda_f32(scales, "decode_stage_a(scales)")
+    n, c, h, w = means.shape
+    if q0.dtype != torch.int32 or tuple(q0.shape) != (n, c // 2, h, w) or not q0.is_contiguous():
+        raise nat.DvcError("decode_stage_a: q0 must be contiguous int32 [N, C/2, H, W]")
+    params = torch.empty((n, 3 * c, h, w), dtype=torch.float32, device=means.device)
+    with nat.device_of(means):
+        rc = nat.lib().dvc_dual_prior_decode_stage_a(
+            q0.data_ptr(), means.data_ptr(), scales.data_ptr(), params.data_ptr(), n, c, h, w,
+            nat.st4(means), nat.st4(scales), nat.st4(params), nat.stream_of(means))
+    nat.check(rc, "dvc_dual_prior_decode_stage_a")
+    return params
+
+
+def decode_stage_b(q0, q1, means, prior):
+    """``y_hat`` of the decoder (video_model.py:284-289 == :459-464)."""
+    means = nat.require_cuda_f32(means, "decode_stage_b(means)")
+    prior = nat.require_cuda_f32(prior, "decode_stage_b(prior)")
+    n, c, h, w = means.shape
+    for q in (q0, q1):
+        if q.dtype != torch.int32 or tuple(q.shape) != (n, c // 2, h, w) or not q.is_contiguous():
+            raise nat.DvcError("decode_stage_b: q0/q1 must be contiguous int32 [N, C/2, H, W]")
+    if tuple(prior.shape) != (n, 2 * c, h, w):
+        raise nat.DvcError("decode_stage_b: prior must be [N, 2C, H, W]")
+    y_hat = torch.empty((n, c, h, w), dtype=torch.float32, device=means.device)
+    with nat.device_of(means):
+        rc = nat.lib().dvc_dual_prior_decode_stage_b(
+            q0.data_ptr(), q1.data_ptr(), means.data_ptr(), prior.data_ptr(), y_hat.data_ptr(),
+            n, c, h, w, nat.st4(means), nat.st4(prior), nat.st4(y_hat), nat.stream_of(means))
+    nat.check(rc, "dvc_dual_prior_decode_stage_b")
+    return y_hat

@@ -23,7 +23,9 @@ from . import _native as nat
 from .entropy_models import _launch_noise_like, eb_forward
 
 __all__ = ["dual_prior_stage_a", "dual_prior_stage_b_gc", "forward_dual_prior",
-           "motion_context_forward", "frame_context_forward"]
+           "motion_context_forward", "frame_context_forward",
+           "motion_context_compress", "frame_context_compress",
+           "motion_context_decompress", "frame_context_decompress"]
 
 
 def _check_latents(y, means, scales, who):
@@ -221,3 +223,129 @@ def frame_context_forward(self, y, y_ref, context):
     means_hat, scales_hat = self.y_prior_fusion(
         torch.cat((temporal_params, params, y_ref), dim=1)).chunk(2, 1)
     return _context_tail(self, y, means_hat, scales_hat, z_likelihoods)
+
+
+# ---------------------------------------------------------------------------
+# real bit streams: drop-ins for compress / decompress
+# of both context models (video_model.py:236-291, :408-466)
+# ---------------------------------------------------------------------------
+def _coder_tables(module):
+    from . import coder
+    return coder.Tables(module._quantized_cdf, module._cdf_length, module._offset)
+
+
+def _medians(eb):
+    return eb._get_medians().detach().reshape(1, -1, 1, 1)
+
+
+def _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending):
+    """stage A -> spatial prior -> stage B (compress planes) -> two encoder
+    launches with the table look-up fused -> ONE device->host transfer for the
+    three strings.  The reference does 2 build_indexes (63 passes each), 3
+    compress calls (device->host copy + ``.tolist()`` + CPU coder each) and a
+    decompress of z just to obtain z_hat (:238-251)."""
+    from . import coder
+    gc = self.gaussian_conditional
+    params = dual_prior_stage_a(y, means_hat, scales_hat)
+    prior = self.y_spatial_prior(params)
+    y_hat, _, _, _, planes = dual_prior_stage_b_gc(
+        y, means_hat, scales_hat, prior, gc, training=False, compress=True)
+    q_w0, q_w1, s_w0, s_w1 = planes
+    tables = _coder_tables(gc)
+    sb, _ = _gc_bounds(gc)
+    p0 = coder.rans_encode_async(tables, x=q_w0, scales=s_w0, scale_table=gc.scale_table,
+                                 scale_bound=sb)
+    p1 = coder.rans_encode_async(tables, x=q_w1, scales=s_w1, scale_table=gc.scale_table,
+                                 scale_bound=sb)
+    y_strings_0, y_strings_1, z_strings = coder.collect([p0, p1, z_pending])
+    return y_hat, {"strings": [y_strings_0, y_strings_1, z_strings], "shape": z.size()[-2:]}
+
+
+def _compress_head(self, y):
+    from . import coder
+    eb = self.entropy_bottleneck
+    z = self.hyper_encoder(y)
+    z_pending = coder.rans_encode_async(_coder_tables(eb), x=z, means=_medians(eb).expand_as(z))
+    # z_hat = decompress(compress(z)) = round(z - median) + median: the likelihood
+    # kernel's z_hat output (bit-identical, tests/test_gpu_coder.py)
+    _, z_hat, _ = eb_forward(eb, z, training=False, want_outputs=False, want_zhat=True)
+    return z, z_hat, z_pending
+
+
+def motion_context_compress(self, y, y_ref):
+    """Drop-in for ``MotionContextModel.compress`` (video_model.py:236-253)."""
+    z, z_hat, z_pending = _compress_head(self, y)
+    params = self.hyper_decoder(z_hat)
+    if y_ref is None:
+        y_ref = torch.zeros_like(y)
+    means_hat, scales_hat = self.y_prior_fusion(torch.cat((params, y_ref), dim=1)).chunk(2, 1)
+    return _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending)
+
+
+def frame_context_compress(self, y, y_ref, context):
+    """Drop-in for ``FrameContextModel.compress`` (video_model.py:408-427)."""
+    z, z_hat, z_pending = _compress_head(self, y)
+    params = self.hyper_decoder(z_hat)
+    if y_ref is None:
+        y_ref = torch.zeros_like(y)
+    temporal_params = self.temporal_prior_encoder(context)
+    means_hat, scales_hat = self.y_prior_fusion(
+        torch.cat((temporal_params, params, y_ref), dim=1)).chunk(2, 1)
+    return _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending)
+
+
+def _decompress_head(self, strings, shape):
+    from . import coder
+    assert isinstance(strings, list) and len(strings) == 3
+    eb = self.entropy_bottleneck
+    tables = _coder_tables(eb)
+    out_shape = (len(strings[2]), tables.cdf.size(0), int(shape[0]), int(shape[1]))
+    return coder.rans_decode(strings[2], tables, out_shape, means=_medians(eb),
+                             device=tables.cdf.device)
+
+
+def _decompress_tail(self, strings, means_hat, scales_hat):
+    """Two decoding passes around the spatial prior (video_model.py:259-289):
+    the checkerboard scale planes are read in place by the decoder (no masks, no
+    build_indexes tensor), symbols stay int32 on the device, and two
+    element-wise kernels replace the ~20 mask multiplies / adds / cats."""
+    from . import coder
+    gc = self.gaussian_conditional
+    tables = _coder_tables(gc)
+    sb, _ = _gc_bounds(gc)
+    n, c, h, w = means_hat.shape
+    _check_latents(means_hat, means_hat, scales_hat, "decompress")
+    half = c // 2
+    q0 = coder.rans_decode(strings[0], tables, (n, half, h, w), scales=scales_hat[:, :half],
+                           scale_table=gc.scale_table, scale_bound=sb, want_symbols=True,
+                           cb=(0, half * scales_hat.stride(1)), device=means_hat.device)
+    params = coder.decode_stage_a(q0, means_hat, scales_hat)
+    prior = self.y_spatial_prior(params)
+    q1 = coder.rans_decode(strings[1], tables, (n, half, h, w), scales=prior[:, half:c],
+                           scale_table=gc.scale_table, scale_bound=sb, want_symbols=True,
+                           cb=(1, c * prior.stride(1)), device=means_hat.device)
+    return coder.decode_stage_b(q0, q1, means_hat, prior)
+
+
+def motion_context_decompress(self, strings, shape, y_ref):
+    """Drop-in for ``MotionContextModel.decompress`` (video_model.py:255-291)."""
+    z_hat = _decompress_head(self, strings, shape)
+    n, _, h, w = z_hat.shape
+    params = self.hyper_decoder(z_hat)
+    if y_ref is None:
+        y_ref = torch.zeros([n, params.size(1) // 2, h * 4, w * 4], device=z_hat.device)
+    means_hat, scales_hat = self.y_prior_fusion(torch.cat((params, y_ref), dim=1)).chunk(2, 1)
+    return _decompress_tail(self, strings, means_hat, scales_hat)
+
+
+def frame_context_decompress(self, strings, shape, y_ref, context):
+    """Drop-in for ``FrameContextModel.decompress`` (video_model.py:429-466)."""
+    z_hat = _decompress_head(self, strings, shape)
+    n, _, h, w = z_hat.shape
+    params = self.hyper_decoder(z_hat)
+    if y_ref is None:
+        y_ref = torch.zeros([n, params.size(1) // 2, h * 4, w * 4], device=z_hat.device)
+    temporal_params = self.temporal_prior_encoder(context)
+    means_hat, scales_hat = self.y_prior_fusion(
+        torch.cat((temporal_params, params, y_ref), dim=1)).chunk(2, 1)
+    return _decompress_tail(self, strings, means_hat, scales_hat)

@@ -72,6 +72,11 @@ struct Source {             // where symbols and indexes come from
   CTS xs, ms, ss;
   int C, H, W, HW;
   long long L;              // symbols per sample = C*H*W
+  // checkerboard pairing of the scale planes (decoder, video_model.py:268, :281):
+  // positions whose (h + w) parity differs from cb_parity read `cb_alt`
+  // elements further (the other channel half); cb_parity < 0: off
+  int cb_parity;
+  long long cb_alt;
 };
 
 // GaussianConditional.build_indexes for one scale: s = max(scale, bound);
@@ -106,9 +111,11 @@ __device__ __forceinline__ int fetch_symbol(const Source& s, int n, long long e,
 __device__ __forceinline__ int fetch_index(const Source& s, int n, long long e, int c, int h,
                                            int w, const float* tab) {
   if (s.indexes) return __ldg(s.indexes + n * s.L + e);
-  if (s.scales)
-    return scale_index(__ldg(s.scales + n * s.ss.n + c * s.ss.c + h * s.ss.h + w * s.ss.w),
-                       s.scale_bound, tab, s.T);
+  if (s.scales) {
+    long long o = n * s.ss.n + c * s.ss.c + h * s.ss.h + w * s.ss.w;
+    if (s.cb_parity >= 0 && ((h + w) & 1) != s.cb_parity) o += s.cb_alt;
+    return scale_index(__ldg(s.scales + o), s.scale_bound, tab, s.T);
+  }
   return c;  // EntropyBottleneck._build_indexes: the channel
 }
 
@@ -497,6 +504,72 @@ __global__ void __launch_bounds__(kCoderWarps * 32) rans_decode_kernel(const Dec
   if (p.status && __any_sync(0xffffffffu, bad) && lane == 0) atomicExch(p.status, 1);
 }
 
+// ---------------------------------------------------------------------------
+// Decoder side of the checkerboard dual prior (video_model.py:259-289 ==
+// :433-464): element-wise glue between the two decoding passes and the
+// spatial-prior conv.  q0 / q1 are the decoded symbol planes [N, C/2, H, W]
+// (int32, contiguous).  Selection replaces the reference's multiply-by-mask and
+// add-of-zero (equal values; zero signs may differ).
+// ---------------------------------------------------------------------------
+struct DecStageP {
+  const int32_t* q0;
+  const int32_t* q1;
+  const float* means;   // [N, C, H, W]
+  const float* scales;  // stage a: [N, C, H, W]
+  const float* prior;   // stage b: [N, 2C, H, W] = (means_0, scales_0, means_1, scales_1)
+  float* out;           // stage a: params [N, 3C, H, W]; stage b: y_hat [N, C, H, W]
+  CTS ms, ss, ps, os;
+  int N, C, H, W;
+};
+
+// params = cat((q0 + means_0) * mask_0, (q0 + means_1) * mask_1, means, scales)
+__global__ void __launch_bounds__(256) decode_stage_a_kernel(const DecStageP p) {
+  const int half = p.C >> 1, HW = p.H * p.W;
+  const long long per = (long long)p.C * HW, total = per * p.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per);
+    const int r = (int)(i - n * per);
+    const int c = r / HW, r2 = r - c * HW, h = r2 / p.W, w = r2 - h * p.W;
+    const float m = __ldg(p.means + n * p.ms.n + c * p.ms.c + h * p.ms.h + w * p.ms.w);
+    const float s = __ldg(p.scales + n * p.ss.n + c * p.ss.c + h * p.ss.h + w * p.ss.w);
+    const int cq = c < half ? c : c - half;
+    const bool mine = (((h + w) & 1) == 0) == (c < half);  // first half: even cells, second: odd
+    float v = 0.f;
+    if (mine) v = add_rn((float)__ldg(p.q0 + ((long long)(n * half + cq) * p.H + h) * p.W + w), m);
+    float* o = p.out + n * p.os.n + h * p.os.h + w * p.os.w;
+    o[c * p.os.c] = v;
+    o[(p.C + c) * p.os.c] = m;
+    o[(2 * p.C + c) * p.os.c] = s;
+  }
+}
+
+// y_hat = cat(y_hat_0_0 + y_hat_0_1, y_hat_1_1 + y_hat_1_0)
+__global__ void __launch_bounds__(256) decode_stage_b_kernel(const DecStageP p) {
+  const int half = p.C >> 1, HW = p.H * p.W;
+  const long long per = (long long)p.C * HW, total = per * p.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per);
+    const int r = (int)(i - n * per);
+    const int c = r / HW, r2 = r - c * HW, h = r2 / p.W, w = r2 - h * p.W;
+    const int cq = c < half ? c : c - half;
+    const bool anchor = (((h + w) & 1) == 0) == (c < half);
+    const long long qo = ((long long)(n * half + cq) * p.H + h) * p.W + w;
+    float v;
+    if (anchor) {
+      v = add_rn((float)__ldg(p.q0 + qo),
+                 __ldg(p.means + n * p.ms.n + c * p.ms.c + h * p.ms.h + w * p.ms.w));
+    } else {
+      // spatial-prior means: chunk 0 (first half) or chunk 2 (second half) of `prior`
+      const int pc = c < half ? cq : 2 * half + cq;
+      v = add_rn((float)__ldg(p.q1 + qo),
+                 __ldg(p.prior + n * p.ps.n + pc * p.ps.c + h * p.ps.h + w * p.ps.w));
+    }
+    p.out[n * p.os.n + c * p.os.c + h * p.os.h + w * p.os.w] = v;
+  }
+}
+
 static int fill_source(Source& s, const int32_t* symbols, const float* x, const float* means,
                        const int32_t* indexes, const float* scales, const float* scale_table,
                        int64_t T, float scale_bound, int64_t C, int64_t H, int64_t W,
@@ -515,6 +588,8 @@ static int fill_source(Source& s, const int32_t* symbols, const float* x, const 
   s.xs = cts(x_st); s.ms = cts(means_st); s.ss = cts(scales_st);
   s.C = (int)C; s.H = (int)H; s.W = (int)W; s.HW = (int)(H * W);
   s.L = (long long)C * H * W;
+  s.cb_parity = -1;
+  s.cb_alt = 0;
   return DVC_OK;
 }
 
@@ -684,8 +759,11 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
                     const int32_t* offset, int64_t n_cdf, int64_t cdf_stride, const float* means,
                     float* out, int32_t* out_symbols, int* status, int64_t N, int64_t C,
                     int64_t H, int64_t W, const int64_t scales_st[4], const int64_t means_st[4],
-                    const int64_t out_st[4], int64_t stream_symbols, dvc_stream_t stream) {
+                    const int64_t out_st[4], int64_t stream_symbols, int cb_parity,
+                    int64_t cb_alt, dvc_stream_t stream) {
   DVC_REQUIRE(in && in_bytes, "rans_decode: null input");
+  DVC_REQUIRE(cb_parity < 0 || (cb_parity <= 1 && scales),
+              "rans_decode: cb_parity must be -1, or 0/1 together with scales");
   DVC_REQUIRE(out || out_symbols, "rans_decode: nothing to write");
   DVC_REQUIRE(!out || out_st, "rans_decode: out without strides");
   DVC_REQUIRE(N > 0 && N <= 65535, "rans_decode: N must be in [1, 65535]");
@@ -695,6 +773,8 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
   int rc = fill_source(p.src, nullptr, nullptr, means, indexes, scales, scale_table, T,
                        scale_bound, C, H, W, nullptr, means_st, scales_st, "rans_decode");
   if (rc) return rc;
+  p.src.cb_parity = cb_parity < 0 ? -1 : cb_parity;
+  p.src.cb_alt = cb_alt;
   rc = fill_tables(p.tb, cdf, cdf_size, offset, n_cdf, cdf_stride, "rans_decode");
   if (rc) return rc;
   Partition q;
@@ -708,6 +788,46 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
   dim3 grid((unsigned)((q.n_streams + kCoderWarps - 1) / kCoderWarps), (unsigned)N);
   rans_decode_kernel<<<grid, kCoderWarps * 32, 0, (cudaStream_t)stream>>>(p);
   return check_launch("rans_decode_kernel");
+}
+
+static int launch_dec_stage(DecStageP& p, int64_t N, int64_t C, int64_t H, int64_t W, bool stage_a,
+                            dvc_stream_t stream, const char* who) {
+  DVC_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "%s: empty tensor", who);
+  DVC_REQUIRE((C % 2) == 0 && (H % 2) == 0 && (W % 2) == 0, "%s: C, H, W must be even", who);
+  DVC_REQUIRE((long long)C * H * W < 2147483647LL / 3, "%s: C*H*W too large", who);
+  p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W;
+  const long long total = (long long)N * C * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (stage_a) decode_stage_a_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  else decode_stage_b_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch(who);
+}
+
+int dvc_dual_prior_decode_stage_a(const int32_t* q0, const float* means, const float* scales,
+                                  float* params, int64_t N, int64_t C, int64_t H, int64_t W,
+                                  const int64_t means_st[4], const int64_t scales_st[4],
+                                  const int64_t params_st[4], dvc_stream_t stream) {
+  DVC_REQUIRE(q0 && means && scales && params && means_st && scales_st && params_st,
+              "dual_prior_decode_stage_a: null pointer");
+  DecStageP p;
+  p.q0 = q0; p.q1 = nullptr; p.means = means; p.scales = scales; p.prior = nullptr; p.out = params;
+  p.ms = cts(means_st); p.ss = cts(scales_st); p.ps = cts(nullptr); p.os = cts(params_st);
+  return launch_dec_stage(p, N, C, H, W, true, stream, "dual_prior_decode_stage_a");
+}
+
+int dvc_dual_prior_decode_stage_b(const int32_t* q0, const int32_t* q1, const float* means,
+                                  const float* prior, float* y_hat, int64_t N, int64_t C,
+                                  int64_t H, int64_t W, const int64_t means_st[4],
+                                  const int64_t prior_st[4], const int64_t y_hat_st[4],
+                                  dvc_stream_t stream) {
+  DVC_REQUIRE(q0 && q1 && means && prior && y_hat && means_st && prior_st && y_hat_st,
+              "dual_prior_decode_stage_b: null pointer");
+  DecStageP p;
+  p.q0 = q0; p.q1 = q1; p.means = means; p.scales = nullptr; p.prior = prior; p.out = y_hat;
+  p.ms = cts(means_st); p.ss = cts(nullptr); p.ps = cts(prior_st); p.os = cts(y_hat_st);
+  return launch_dec_stage(p, N, C, H, W, false, stream, "dual_prior_decode_stage_b");
 }
 
 }  // extern "C"

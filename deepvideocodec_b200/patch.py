@@ -15,6 +15,8 @@ reference name (dmc/models/...)                        replacement
 ``FrameContextModel.forward_dual_prior`` (:341)        ``context.forward_dual_prior``
 ``MotionContextModel.forward`` (:218)                  ``context.motion_context_forward``
 ``FrameContextModel.forward`` (:390)                   ``context.frame_context_forward``
+``MotionContextModel.compress/decompress`` (:236/:255) ``context.motion_context_(de)compress``
+``FrameContextModel.compress/decompress`` (:408/:429)  ``context.frame_context_(de)compress``
 ``DMC.motion_compensation`` (:497)                     fused 2-launch version below
 ``train.collect_likelihoods_list`` (train.py:74)       ``rate.collect_likelihoods_list``
 =====================================================  =========================================
@@ -83,6 +85,10 @@ def patch(models_pkg, train_module=None, fuse_context_models=True):
     if fuse_context_models:
         _set(vm.MotionContextModel, "forward", context.motion_context_forward)
         _set(vm.FrameContextModel, "forward", context.frame_context_forward)
+        _set(vm.MotionContextModel, "compress", context.motion_context_compress)
+        _set(vm.FrameContextModel, "compress", context.frame_context_compress)
+        _set(vm.MotionContextModel, "decompress", context.motion_context_decompress)
+        _set(vm.FrameContextModel, "decompress", context.frame_context_decompress)
     _set(vm.DMC, "motion_compensation", _motion_compensation)
     if train_module is not None:
         _set(train_module, "collect_likelihoods_list", rate.collect_likelihoods_list)

@@ -376,7 +376,41 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes,
                     float* out, int32_t* out_symbols, int* status, int64_t N,
                     int64_t C, int64_t H, int64_t W, const int64_t scales_st[4],
                     const int64_t means_st[4], const int64_t out_st[4],
-                    int64_t stream_symbols, dvc_stream_t stream);
+                    int64_t stream_symbols, int cb_parity, int64_t cb_alt,
+                    dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Decoder side of the checkerboard dual prior: the element-wise glue of
+ * MotionContextModel.decompress / FrameContextModel.decompress
+ * (video_model.py:259-289 == :433-464) around the spatial-prior conv.
+ *
+ * dvc_rans_decode(cb_parity, cb_alt): the reference builds the scale plane of a
+ * decoding pass as `scales_a * mask_p + scales_b * mask_q` (:268, :281) before
+ * build_indexes.  With cb_parity = 0/1 the decoder reads scales[...] where
+ * (h + w) & 1 == cb_parity and scales[... + cb_alt] (element offset; the other
+ * channel group) elsewhere -- no mask tensors, no plane.  cb_parity = -1: off.
+ *
+ * stage a (:274-277): params [N,3C,H,W] = cat((q0 + means_0) * mask_0,
+ *     (q0 + means_1) * mask_1, means, scales)  -- the spatial-prior conv input.
+ * stage b (:284-289): y_hat [N,C,H,W] from q0, q1, means and the conv output
+ *     prior [N,2C,H,W] = (means_0', scales_0', means_1', scales_1').
+ * q0, q1: decoded symbols, int32, contiguous [N, C/2, H, W] (dvc_rans_decode's
+ * out_symbols).  C, H, W even.
+ * ------------------------------------------------------------------------- */
+int dvc_dual_prior_decode_stage_a(const int32_t* q0, const float* means,
+                                  const float* scales, float* params, int64_t N,
+                                  int64_t C, int64_t H, int64_t W,
+                                  const int64_t means_st[4],
+                                  const int64_t scales_st[4],
+                                  const int64_t params_st[4],
+                                  dvc_stream_t stream);
+int dvc_dual_prior_decode_stage_b(const int32_t* q0, const int32_t* q1,
+                                  const float* means, const float* prior,
+                                  float* y_hat, int64_t N, int64_t C, int64_t H,
+                                  int64_t W, const int64_t means_st[4],
+                                  const int64_t prior_st[4],
+                                  const int64_t y_hat_st[4],
+                                  dvc_stream_t stream);
 
 #ifdef __cplusplus
 }

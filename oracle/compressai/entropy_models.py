@@ -27,6 +27,27 @@ import torch.nn.functional as F
 from .ops import LowerBound
 
 
+def _rans():
+    """``oracle/rans.py`` -- also when this package is imported as top-level
+    ``compressai`` (the way the stock reference sees it)."""
+    try:
+        from .. import rans
+        return rans
+    except ImportError:
+        import importlib.util
+        import os
+        import sys
+        mod = sys.modules.get("_dvc_oracle_rans")
+        if mod is None:
+            path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                "rans.py")
+            spec = importlib.util.spec_from_file_location("_dvc_oracle_rans", path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["_dvc_oracle_rans"] = mod
+            spec.loader.exec_module(mod)
+        return mod
+
+
 class EntropyModel(nn.Module):
     def __init__(self, likelihood_bound: float = 1e-9, entropy_coder=None,
                  entropy_coder_precision: int = 16):
@@ -74,7 +95,7 @@ class EntropyModel(nn.Module):
         return outputs
 
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
-        from .. import rans
+        rans = _rans()
         cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32,
                           device=pmf.device)
         for i, p in enumerate(pmf):
@@ -103,7 +124,7 @@ class EntropyModel(nn.Module):
             raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
 
     def compress(self, inputs, indexes, means=None):
-        from .. import rans
+        rans = _rans()
         symbols = self.quantize(inputs, "symbols", means)
         if len(inputs.size()) < 2:
             raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
@@ -124,7 +145,7 @@ class EntropyModel(nn.Module):
         return strings
 
     def decompress(self, strings, indexes, dtype=torch.float, means=None):
-        from .. import rans
+        rans = _rans()
         if not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         if not len(strings) == indexes.size(0):

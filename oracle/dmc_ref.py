@@ -145,6 +145,41 @@ def context_model_forward(y, z, means, scales, spatial_prior, eb, gc):
     return y_hat, z_hat, {"y": y_lik, "z": z_lik}
 
 
+def context_model_compress(y, z, prior_fusion, spatial_prior, eb, gc):
+    """Non-conv part of ``MotionContextModel.compress`` / ``FrameContextModel
+    .compress`` (video_model.py:236-253 / :408-427).  ``prior_fusion(z_hat)``
+    stands for the conv stack between ``z_hat`` and ``(means, scales)``
+    (hyper decoder, temporal prior, ``y_prior_fusion`` + ``chunk``)."""
+    z_strings = eb.compress(z)
+    z_hat = eb.decompress(z_strings, z.size()[-2:])
+    means, scales = prior_fusion(z_hat)
+    y_hat, q_w0, q_w1, s_w0, s_w1 = dual_prior(y, means, scales, spatial_prior, mode="compress")
+    indexes_0 = gc.build_indexes(s_w0)
+    indexes_1 = gc.build_indexes(s_w1)
+    y_strings_0 = gc.compress(q_w0, indexes_0)
+    y_strings_1 = gc.compress(q_w1, indexes_1)
+    return y_hat, {"strings": [y_strings_0, y_strings_1, z_strings], "shape": z.size()[-2:]}
+
+
+def context_model_decompress(strings, shape, prior_fusion, spatial_prior, eb, gc):
+    """Non-conv part of ``MotionContextModel.decompress`` / ``FrameContextModel
+    .decompress`` (video_model.py:255-291 / :429-466)."""
+    assert isinstance(strings, list) and len(strings) == 3
+    z_hat = eb.decompress(strings[2], shape)
+    means, scales = prior_fusion(z_hat)
+    m0, m1 = checkerboard_masks(means.size(2), means.size(3), means.device)
+    mu0, mu1 = means.chunk(2, 1)
+    s0, s1 = scales.chunk(2, 1)
+    q_r0 = gc.decompress(strings[0], gc.build_indexes(s0 * m0 + s1 * m1))
+    y00 = (q_r0 + mu0) * m0
+    y11 = (q_r0 + mu1) * m1
+    mu0p, s0p, mu1p, s1p = spatial_prior(torch.cat((y00, y11, means, scales), dim=1)).chunk(4, 1)
+    q_r1 = gc.decompress(strings[1], gc.build_indexes(s0p * m1 + s1p * m0))
+    y01 = (q_r1 + mu0p) * m1
+    y10 = (q_r1 + mu1p) * m0
+    return torch.cat((y00 + y01, y11 + y10), dim=1)
+
+
 # --------------------------------------------------------------------------
 # piece 4: rate  (dmc/train.py:74-93)
 # --------------------------------------------------------------------------

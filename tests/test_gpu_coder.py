@@ -318,3 +318,132 @@ def test_reference_compress_call_sequence(cuda_dev, gc_pair):
         assert torch.equal(r1, q1)
         y01, y10 = (r1 + pm0) * mask_1, (r1 + pm1) * mask_0
         assert torch.equal(torch.cat((y00 + y01, y11 + y10), 1), y_hat)
+
+
+# ---------------------------------------------------------------------------
+# context-model level: fused compress / decompress drop-ins vs the oracle's
+# restatement of the reference's methods, executed by CUDA eager on this device
+# ---------------------------------------------------------------------------
+class _Ctx(torch.nn.Module):
+    """Stand-in with the attribute names of the reference's context models
+    (video_model.py:128-150 / :294-322) and small conv stacks."""
+
+    def __init__(self, c, cz, frame, gc, eb):
+        super().__init__()
+        conv = torch.nn.Conv2d
+        self.hyper_encoder = torch.nn.Sequential(conv(c, cz, 3, 2, 1), torch.nn.LeakyReLU(0.1),
+                                                 conv(cz, cz, 3, 2, 1))
+        self.hyper_decoder = torch.nn.Sequential(
+            torch.nn.ConvTranspose2d(cz, c, 4, 2, 1), torch.nn.LeakyReLU(0.1),
+            torch.nn.ConvTranspose2d(c, c, 4, 2, 1))
+        extra = c if frame else 0
+        self.y_prior_fusion = conv(2 * c + extra, 2 * c, 3, 1, 1)
+        self.y_spatial_prior = conv(3 * c, 2 * c, 3, 1, 1)
+        if frame:
+            self.temporal_prior_encoder = conv(8, c, 3, 4, 1)
+        self.gaussian_conditional = gc
+        self.entropy_bottleneck = eb
+
+
+@pytest.mark.parametrize("frame", [False, True])
+@pytest.mark.parametrize("S", [0, 256])
+def test_context_model_compress_decompress(cuda_dev, gc_pair, frame, S, monkeypatch):
+    import deepvideocodec_b200 as dvc
+    from deepvideocodec_b200 import coder
+    from oracle import dmc_ref
+    from oracle.compressai import entropy_models as oem
+    monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", S)
+    o_gc, p_gc = gc_pair
+    torch.manual_seed(31)
+    o_eb = oem.EntropyBottleneck(6)
+    torch.manual_seed(31)
+    p_eb = dvc.EntropyBottleneck(6)
+    o_eb.update()
+    p_eb.update()
+    torch.manual_seed(32)
+    m = _Ctx(12, 6, frame, p_gc, p_eb).to(cuda_dev).eval()
+    o_eb = o_eb.to(cuda_dev)
+    o_gc_dev = oem.GaussianConditional(None)
+    o_gc_dev.update_scale_table(_scale_table())
+    o_gc_dev = o_gc_dev.to(cuda_dev)
+    g = torch.Generator().manual_seed(33)
+    y = (torch.randn(2, 12, 16, 24, generator=g) * 5).to(cuda_dev)
+    y_ref = torch.randn(2, 12, 16, 24, generator=g).to(cuda_dev)
+    context = torch.randn(2, 8, 64, 96, generator=g).to(cuda_dev)
+
+    def prior_fusion(z_hat):
+        params = m.hyper_decoder(z_hat)
+        parts = (m.temporal_prior_encoder(context), params, y_ref) if frame else (params, y_ref)
+        return m.y_prior_fusion(torch.cat(parts, 1)).chunk(2, 1)
+
+    with torch.no_grad():
+        if frame:
+            y_hat, out = dvc.frame_context_compress(m, y, y_ref, context)
+            dec = dvc.frame_context_decompress(m, out["strings"], out["shape"], y_ref, context)
+        else:
+            y_hat, out = dvc.motion_context_compress(m, y, y_ref)
+            dec = dvc.motion_context_decompress(m, out["strings"], out["shape"], y_ref)
+        z = m.hyper_encoder(y)
+        y_hat_o, out_o = dmc_ref.context_model_compress(
+            y, z, prior_fusion, m.y_spatial_prior, o_eb, o_gc_dev)
+        dec_o = dmc_ref.context_model_decompress(
+            out_o["strings"], out_o["shape"], prior_fusion, m.y_spatial_prior, o_eb, o_gc_dev)
+    assert torch.equal(y_hat, y_hat_o)
+    assert torch.equal(dec, y_hat) and torch.equal(dec_o, y_hat_o)
+    assert tuple(out["shape"]) == tuple(out_o["shape"])
+    assert [len(s) for s in out["strings"]] == [2, 2, 2]
+    if S == 0:
+        assert out["strings"] == out_o["strings"]            # byte-identical to the stock streams
+    else:
+        # the fused decoder also decodes the oracle's stock streams
+        with torch.no_grad():
+            fn = dvc.frame_context_decompress if frame else dvc.motion_context_decompress
+            extra = (context,) if frame else ()
+            assert torch.equal(fn(m, out_o["strings"], out_o["shape"], y_ref, *extra), y_hat)
+
+
+def test_golden_reference_bitstreams(cuda_dev, golden_dir):
+    """Vectors written by the reference's own ``MotionContextModel.compress``
+    (tests/golden/make_golden_coder.py): same tensors in -> same bytes out."""
+    import os
+    import deepvideocodec_b200 as dvc
+    from deepvideocodec_b200 import coder
+    z = np.load(os.path.join(golden_dir, "coder.npz"))
+    t = lambda k: torch.from_numpy(z[k]).to(cuda_dev)      # noqa: E731
+    gc = dvc.GaussianConditional(None)
+    gc.update_scale_table(z["scale_table"].tolist())
+    assert np.array_equal(gc._quantized_cdf.numpy(), z["gc.cdf"])
+    assert np.array_equal(gc._cdf_length.numpy(), z["gc.len"])
+    assert np.array_equal(gc._offset.numpy(), z["gc.off"])
+    gc = gc.to(cuda_dev)
+    eb = dvc.EntropyBottleneck(8)
+    eb.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ebp.")},
+                       strict=False)
+    eb.update(force=True)
+    assert np.array_equal(eb._quantized_cdf.numpy(), z["eb.cdf"])
+    assert np.array_equal(eb._offset.numpy(), z["eb.off"])
+    eb = eb.to(cuda_dev)
+    strs = lambda name: [z[f"str.{name}.{n}"].tobytes() for n in range(2)]   # noqa: E731
+    assert torch.equal(gc.build_indexes(t("s0")).cpu(), torch.from_numpy(z["i0"]))
+    assert torch.equal(gc.build_indexes(t("s1")).cpu(), torch.from_numpy(z["i1"]))
+    raw = dict(stream_symbols=0)
+    assert coder.rans_encode(gc._tables(), x=t("q0"), scales=t("s0"), scale_table=gc.scale_table,
+                             **raw) == strs("y0")
+    assert coder.rans_encode(gc._tables(), x=t("q1"), indexes=t("i1"), **raw) == strs("y1")
+    med = eb._get_medians().detach().reshape(1, -1, 1, 1)
+    assert coder.rans_encode(eb._tables(), x=t("z"), means=med.expand_as(t("z")), **raw) == strs("z")
+    assert torch.equal(eb.decompress(strs("z"), tuple(z["shape"])).cpu(), torch.from_numpy(z["z_hat"]))
+    assert torch.equal(gc.decompress(strs("y0"), t("i0")).cpu(), torch.from_numpy(z["q0"]))
+    # decoder glue against the reference's tensors
+    means, scales, prior = t("means"), t("scales"), t("prior")
+    n, c, h, w = means.shape
+    q0 = coder.rans_decode(strs("y0"), gc._tables(), (n, c // 2, h, w), scales=scales[:, :c // 2],
+                           scale_table=gc.scale_table, want_symbols=True,
+                           cb=(0, (c // 2) * scales.stride(1)))
+    assert torch.equal(q0.float().cpu(), torch.from_numpy(z["q0"]))
+    q1 = coder.rans_decode(strs("y1"), gc._tables(), (n, c // 2, h, w), scales=prior[:, c // 2:c],
+                           scale_table=gc.scale_table, want_symbols=True,
+                           cb=(1, c * prior.stride(1)))
+    assert torch.equal(q1.float().cpu(), torch.from_numpy(z["q1"]))
+    y_hat = coder.decode_stage_b(q0, q1, means, prior)
+    assert torch.equal(y_hat.cpu(), torch.from_numpy(z["y_hat"]))

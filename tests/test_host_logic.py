@@ -29,10 +29,18 @@ def test_entropy_module_surface_matches_compressai_names():
     assert torch.isfinite(eb.loss())
     with pytest.raises(NotImplementedError):
         dvc.EntropyBottleneck(4, filters=(3, 3))
-    for call in (lambda: eb.update(), lambda: eb.compress(None),
-                 lambda: dvc.GaussianConditional(None).build_indexes(None)):
-        with pytest.raises(NotImplementedError):
-            call()
+    # the entropy-coding surface exists and fails loudly
+    # before update() / on CPU tensors instead of falling back
+    for name in ("update", "compress", "decompress", "_build_indexes", "quantize", "dequantize"):
+        assert callable(getattr(eb, name))
+    gc = dvc.GaussianConditional(None)
+    for name in ("update_scale_table", "update", "build_indexes", "compress", "decompress"):
+        assert callable(getattr(gc, name))
+    with pytest.raises(ValueError, match="update"):
+        eb.compress(torch.zeros(1, 6, 2, 2))
+    assert eb.update() is True and eb._quantized_cdf.dtype == torch.int32
+    with pytest.raises(dvc.DvcError):
+        eb.compress(torch.zeros(1, 6, 2, 2))
 
 
 def test_aux_loss_matches_oracle():

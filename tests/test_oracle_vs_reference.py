@@ -78,6 +78,54 @@ def test_context_models(ref, which):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("which", ["motion", "frame"])
+def test_context_models_real_bitstreams(ref, which):
+    """Stock ``compress`` / ``decompress`` of both context models (the
+    reference's own code, video_model.py:236-291 / :408-466, running over the
+    oracle's CompressAI surface) vs the oracle's non-conv restatement: same
+    strings, same y_hat, and decode(encode) reproduces the encoder's y_hat."""
+    vm = ref["vm"]
+    torch.manual_seed(5)
+    if which == "motion":
+        model = vm.MotionContextModel(ch_mv=8).eval()
+        c = 8
+    else:
+        model = vm.FrameContextModel(N=8, M=12).eval()
+        c = 12
+    model.gaussian_conditional.update_scale_table(
+        sys.modules["models.base_model"].get_scale_table(), force=True)
+    model.entropy_bottleneck.update(force=True)
+    g = torch.Generator().manual_seed(6)
+    y = torch.randn(2, c, 16, 16, generator=g) * 4
+    context = torch.randn(2, 8, 64, 64, generator=g)
+    y_ref = torch.randn(2, c, 16, 16, generator=g)
+
+    def prior_fusion(z_hat):
+        params = model.hyper_decoder(z_hat)
+        if which == "motion":
+            cat = torch.cat((params, y_ref), 1)
+        else:
+            cat = torch.cat((model.temporal_prior_encoder(context), params, y_ref), 1)
+        return model.y_prior_fusion(cat).chunk(2, 1)
+
+    extra = () if which == "motion" else (context,)
+    with torch.no_grad():
+        y_hat_ref, out_ref = model.compress(y, y_ref, *extra)
+        dec_ref = model.decompress(out_ref["strings"], out_ref["shape"], y_ref, *extra)
+        z = model.hyper_encoder(y)
+        y_hat, out = dmc_ref.context_model_compress(
+            y, z, prior_fusion, model.y_spatial_prior, model.entropy_bottleneck,
+            model.gaussian_conditional)
+        dec = dmc_ref.context_model_decompress(
+            out["strings"], out["shape"], prior_fusion, model.y_spatial_prior,
+            model.entropy_bottleneck, model.gaussian_conditional)
+    assert out["strings"] == out_ref["strings"] and tuple(out["shape"]) == tuple(out_ref["shape"])
+    assert torch.equal(y_hat, y_hat_ref)
+    assert torch.equal(dec, dec_ref)
+    assert torch.equal(dec_ref, y_hat_ref)          # the decoder reconstructs the encoder's latents
+    assert all(len(s) == 2 and isinstance(s[0], bytes) for s in out["strings"])
+
+
 def test_rate(ref):
     collect = load_reference_train_fn("collect_likelihoods_list")
     g = torch.Generator().manual_seed(5)
