@@ -28,7 +28,7 @@ __all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "build_indexes",
            "rans_decode", "rans_encode", "rans_encode_async", "stream_symbols_of"]
 
 MAGIC = 0x31435644                     # "DVC1"
-DEFAULT_STREAM_SYMBOLS = int(os.environ.get("DVC_RANS_STREAM_SYMBOLS", "1024"))
+DEFAULT_STREAM_SYMBOLS = int(os.environ.get("DVC_RANS_STREAM_SYMBOLS", "4096"))
 
 
 def _dev_i32(t, name):

@@ -87,7 +87,10 @@ def _stage_b_fwd(y, means, scales, prior, noise, scale_bound, lik_bound, want_pa
     scales_hat = torch.empty_like(y) if want_params else None
     planes = [None] * 4
     if compress:
-        planes = [torch.empty((n, c // 2, h, w), dtype=y.dtype, device=y.device) for _ in range(4)]
+        # the two checkerboard passes are stacked ([2, N, C/2, H, W]) so that one
+        # encoder launch codes both (context._compress_tail)
+        stacked = torch.empty((2, 2, n, c // 2, h, w), dtype=y.dtype, device=y.device)
+        planes = [stacked[0, 0], stacked[0, 1], stacked[1, 0], stacked[1, 1]]
     logsum = torch.empty(n, dtype=torch.float64, device=y.device)
     ws = nat.rate_workspace(y.device, n)
     with nat.device_of(y):
@@ -253,12 +256,26 @@ def _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending):
     q_w0, q_w1, s_w0, s_w1 = planes
     tables = _coder_tables(gc)
     sb, _ = _gc_bounds(gc)
-    p0 = coder.rans_encode_async(tables, x=q_w0, scales=s_w0, scale_table=gc.scale_table,
-                                 scale_bound=sb)
-    p1 = coder.rans_encode_async(tables, x=q_w1, scales=s_w1, scale_table=gc.scale_table,
-                                 scale_bound=sb)
-    y_strings_0, y_strings_1, z_strings = coder.collect([p0, p1, z_pending])
-    return y_hat, {"strings": [y_strings_0, y_strings_1, z_strings], "shape": z.size()[-2:]}
+    n, ch, h, w = q_w0.shape
+    # both passes in ONE launch: the stage-B kernel wrote them as one
+    # [2, N, C/2, H, W] buffer, coded here as a batch of 2N samples
+    q_both, s_both = stacked_planes(planes)
+    pending = coder.rans_encode_async(tables, x=q_both, scales=s_both,
+                                      scale_table=gc.scale_table, scale_bound=sb)
+    y_strings, z_strings = coder.collect([pending, z_pending])
+    return y_hat, {"strings": [y_strings[:n], y_strings[n:], z_strings],
+                   "shape": z.size()[-2:]}
+
+
+def stacked_planes(planes):
+    """``(q_w0, q_w1, s_w0, s_w1)`` of stage B -> ``(q [2N,C/2,H,W], s [2N,C/2,H,W])``
+    without a copy (they are views of one buffer, see ``_stage_b_fwd``)."""
+    q_w0, q_w1, s_w0, s_w1 = planes
+    n, ch, h, w = q_w0.shape
+    base = q_w0._base
+    if base is not None and base.dim() == 6 and s_w1._base is base:
+        return base[0].view(2 * n, ch, h, w), base[1].view(2 * n, ch, h, w)
+    return torch.cat((q_w0, q_w1), 0), torch.cat((s_w0, s_w1), 0)
 
 
 def _compress_head(self, y):

@@ -239,11 +239,19 @@ __global__ void __launch_bounds__(kCoderWarps * 32) rans_encode_kernel(const Enc
     }
     __syncwarp();
     // ---- phase B: the serial chain, last symbol first -------------------------
+    // One lane; the record of symbol i-1 is fetched while symbol i is in the
+    // chain, so only the state update itself is serial: renormalisation test
+    // x >= freq << 47  <=>  (x >> 47) >= freq  (one shift of the high word),
+    // q = mulhi(x, rcp) >> shift, x += bias + q * (2^16 - freq).
     if (lane == 0) {
-      for (int i = cnt - 1; i >= 0; --i) {
-        const uint32_t fs = R.fs[i];
+      int i = cnt - 1;
+      uint32_t fs = R.fs[i], bias = R.bias[i], raw = R.raw[i];
+      unsigned long long rcp = R.rcp[i];
+      while (true) {
+        const int in = i > 0 ? i - 1 : 0;
+        const uint32_t fs_n = R.fs[in], bias_n = R.bias[in], raw_n = R.raw[in];
+        const unsigned long long rcp_n = R.rcp[in];
         if (fs >> 31) {  // bypass: raw nibbles (high first), then their count
-          const uint32_t raw = R.raw[i];
           int nb = 0;
           while (nb < 8 && (raw >> (nb * 4)) != 0) ++nb;
           for (int k = nb - 1; k >= 0; --k) enc_put_bits(x, ptr, (raw >> (k * 4)) & 15u);
@@ -251,12 +259,15 @@ __global__ void __launch_bounds__(kCoderWarps * 32) rans_encode_kernel(const Enc
         }
         const uint32_t freq = fs & 0x1ffffu;
         const uint32_t shift = (fs >> 17) & 31u;
-        if (x >= ((unsigned long long)freq << 47)) {  // Rans64EncPut renormalisation
+        if ((uint32_t)(x >> 47) >= freq) {  // Rans64EncPut renormalisation
           *--ptr = (uint32_t)x;
           x >>= 32;
         }
-        const unsigned long long q = __umul64hi(x, R.rcp[i]) >> shift;
-        x = x + R.bias[i] + q * (unsigned long long)((1u << 16) - freq);
+        const unsigned long long q = __umul64hi(x, rcp) >> shift;
+        x = x + bias + q * (unsigned long long)((1u << 16) - freq);
+        if (i == 0) break;
+        --i;
+        fs = fs_n; bias = bias_n; raw = raw_n; rcp = rcp_n;
       }
     }
     __syncwarp();
