@@ -41,7 +41,8 @@ def nvcc_command(out_path=LIB_PATH, extra=()):
 def build_library(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into ``libdvc_b200.so`` (in-tree)."""
     srcs = [os.path.join(CSRC_DIR, s) for s in SOURCES if os.path.exists(os.path.join(CSRC_DIR, s))]
-    deps = srcs + [os.path.join(CSRC_DIR, "dvc_common.cuh"), os.path.join(INCLUDE_DIR, "dvc_b200.h")]
+    deps = srcs + [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith(".cuh")]
+    deps.append(os.path.join(INCLUDE_DIR, "dvc_b200.h"))
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(d) for d in deps)
         if os.path.getmtime(LIB_PATH) >= newest:
