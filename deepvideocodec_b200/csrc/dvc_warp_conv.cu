@@ -1,0 +1,585 @@
+// dvc_warp_conv.cu -- SURVEY.md row f3: the backward warp of a context feature
+// fused into the 3x3 convolution that consumes it, as a tcgen05 implicit GEMM.
+//
+// Replaces, for one scale of DMC.motion_compensation + MultiScaleContextFusion,
+//   context = flow_warp(ref_feature, mv)                          video_model.py:502-504
+//   conv    = convK_out(torch.cat((context_up, context), dim=1))  video_model.py:55-61
+// (dmc/models/video_model.py; flow_warp is layers.py:175-198).  `context` is
+// still written (the fusion net adds it back as a residual, :64-66) but it is
+// never re-read from HBM: the conv consumes the warped tile straight out of
+// shared memory.
+//
+// GEMM view: D[pixel, co] = sum_{tap, ci} A_tap[pixel, ci] * W[tap, ci, co]
+//   M = 128 consecutive pixels of one image row, N = 64 output channels,
+//   K = 9 taps x Ci input channels, TF32 operands, fp32 accumulation in TMEM.
+//   PyTorch's cuDNN convolution computes in TF32 by default
+//   (torch.backends.cudnn.allow_tf32 = True), so this is the reference's own
+//   arithmetic class; it is not bit-identical to cuDNN (different summation
+//   order) -- tests compare against an fp64 convolution of TF32-truncated
+//   operands and against the fp32 convolution with a TF32 tolerance.
+//
+// Tile: 4 output rows x 128 columns.  Shared memory holds, per pipeline stage,
+// a 16-channel slice of the 6 x 130 input halo in the UMMA no-swizzle K-major
+// layout [k-chunk of 4 channels][halo pixel][4 floats]: a pixel is 16 bytes, 8
+// consecutive pixels are one 128-byte core matrix, so the operand view of tap
+// (dy, dx) for output row r is the SAME buffer with the descriptor start
+// address advanced by ((r + dy) * 130 + dx) * 16 bytes -- no im2col copies.
+// The weights of the slice (9 taps x 16 ci x 64 co) arrive by one bulk copy.
+//
+// Warp roles (448 threads, persistent, one CTA per SM):
+//   warps 0-7  producers: tap records of the tile's halo (op-for-op replay of
+//              flow_warp), then per 16-channel slice either copy `extra` or
+//              gather + blend `feat` into the stage; interior pixels of the
+//              warped slice are also written to `out_warp`;
+//   warps 8-11 epilogue: TMEM -> registers -> + bias -> out_conv, overlapped
+//              with the next tile through the second TMEM accumulator set;
+//   warp 12    MMA issuer (one lane): 72 tcgen05.mma (M128 N64 K8) per slice;
+//   warp 13    weight loader (one lane): cp.async.bulk per slice.
+#include "dvc_common.cuh"
+#include "dvc_warp_math.cuh"
+
+namespace dvc {
+namespace wc {
+
+constexpr int kTileW = 128;   // UMMA M
+constexpr int kRows = 4;      // output rows per tile = accumulators per TMEM set
+constexpr int kCo = 64;       // UMMA N
+constexpr int kChunk = 16;    // input channels per pipeline stage (2 UMMA K-steps of 8)
+constexpr int kHaloW = kTileW + 2;
+constexpr int kHaloH = kRows + 2;
+constexpr int kHaloPix = kHaloW * kHaloH;  // 780
+// pixels per k-chunk plane: >= kHaloPix and == 2 (mod 8), so the 4 k-chunk
+// lanes of two neighbouring pixels (one 8-lane store phase) hit 32 distinct banks
+constexpr int kPlanePix = 786;
+constexpr int kAStageBytes = 4 * kPlanePix * 16;  // 50304
+constexpr int kBStageBytes = 9 * 4 * kCo * 16;    // 36864
+constexpr int kStages = 2;
+constexpr int kProducerWarps = 8, kEpilogueWarps = 4;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 2) * 32;  // 448
+constexpr int kTmemCols = 512;  // 2 sets x 4 accumulators x 64 columns
+
+// shared memory map (bytes)
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + kStages * kAStageBytes;
+constexpr int kOffWgt = kOffB + kStages * kBStageBytes;   // float4[780]
+constexpr int kOffPos = kOffWgt + kHaloPix * 16;          // int[780]
+constexpr int kOffGidx = kOffPos + kHaloPix * 4;          // int[780]
+constexpr int kOffBias = kOffGidx + kHaloPix * 4;         // float[64]
+constexpr int kOffBar = kOffBias + kCo * 4;               // uint64[8]
+constexpr int kOffTmem = kOffBar + 8 * 8;                 // uint32
+constexpr int kSmemBytes = kOffTmem + 16;
+static_assert(kOffBar % 8 == 0 && kOffWgt % 16 == 0 && kOffB % 16 == 0, "smem alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+constexpr int kInterior = 1 << 30;  // gidx flag: the CTA owns this pixel of out_warp
+
+// instruction descriptor: D fp32, A/B TF32, both K-major, N = 64, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kCo >> 3) << 17) |
+                            ((kTileW >> 4) << 24);
+
+struct Params {
+  const float* feat;
+  const float* flow;
+  const float* extra;
+  const float* wpack;
+  const float* bias;
+  float* out_warp;
+  float* out_conv;
+  WarpGeom g;
+  int N, H, W, Cf, Ce;
+  long long fl_n, fl_c, fl_h, fl_w;
+  int flow_level;
+  int tiles_x, tiles_y, n_tiles;
+  int n_chunks_extra, n_chunks;
+  int debug;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A wait that cannot hang the device: a lost arrival traps instead (the host
+// sees cudaErrorLaunchFailure).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void producer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+}
+// 32 lanes x 32 consecutive columns of one TMEM lane quarter -> 32 registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major: rows (pixels / output
+// channels) 16 bytes apart, 8-row core matrices `sbo` bytes apart, the two
+// 16-byte halves of a K = 8 step `lbo` bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
+         ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+struct Tile {
+  int n, y0, x0;
+};
+__device__ __forceinline__ Tile tile_of(const Params& p, int tile) {
+  Tile t;
+  const int tx = tile % p.tiles_x;
+  const int rest = tile / p.tiles_x;
+  t.x0 = tx * kTileW;
+  t.y0 = (rest % p.tiles_y) * kRows;
+  t.n = rest / p.tiles_y;
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// producers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void compute_taps(const Params& p, const Tile& t, int ptid,
+                                             float4* s_wgt, int* s_pos, int* s_gidx) {
+  const int Cf4 = p.Cf >> 2;
+  const float* __restrict__ fl = p.flow + t.n * p.fl_n;
+  for (int q = ptid; q < kHaloPix; q += kProducerThreads) {
+    const int hy = q / kHaloW, hx = q - hy * kHaloW;
+    const int y = t.y0 - 1 + hy, x = t.x0 - 1 + hx;
+    int gi = -1, pos = 0;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+      gi = y * p.W + x;
+      if (hy >= 1 && hy <= kRows && hx >= 1 && hx <= kTileW) gi |= kInterior;
+      const float fx = fetch_flow(fl, p.fl_h, p.fl_w, y, x, p.flow_level);
+      const float fy = fetch_flow(fl + p.fl_c, p.fl_h, p.fl_w, y, x, p.flow_level);
+      const Taps T = make_taps(p.g, y, x, fx, fy);
+      w = make_float4(T.nw, T.ne, T.sw, T.se);
+      pos = (int)((unsigned)((T.y0 * p.W + T.x0) * Cf4) | (T.dx ? kEastIn : 0u) |
+                  (T.dy ? kSouthIn : 0u));
+    }
+    s_wgt[q] = w;
+    s_pos[q] = pos;
+    s_gidx[q] = gi;
+  }
+}
+
+constexpr int kItems = kHaloPix * 4;  // (halo pixel, 4-channel k-chunk) work items per slice
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int chunk, int ptid,
+                                           uint32_t a_stage, const int* s_gidx) {
+  const int Ce4 = p.Ce >> 2;
+  const float4* __restrict__ ex =
+      reinterpret_cast<const float4*>(p.extra) + (long long)t.n * p.H * p.W * Ce4 + chunk * 4;
+#pragma unroll 1
+  for (int base = ptid; base < kItems; base += kProducerThreads * kUnroll) {
+    float4 v[kUnroll];
+    uint32_t dst[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int item = base + u * kProducerThreads;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[u] = 0xffffffffu;
+      if (item < kItems) {
+        const int q = item >> 2, kc = item & 3;
+        dst[u] = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
+        const int gi = s_gidx[q];
+        if (gi >= 0) v[u] = ldg4(ex + (long long)(gi & (kInterior - 1)) * Ce4 + kc);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dst[u] != 0xffffffffu)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(v[u].x),
+                     "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
+                     : "memory");
+  }
+}
+
+__device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int chunk, int ptid,
+                                            uint32_t a_stage, const float4* s_wgt,
+                                            const int* s_pos, const int* s_gidx) {
+  const int Cf4 = p.Cf >> 2;
+  const long long sample = (long long)t.n * p.H * p.W * Cf4;
+  const float4* __restrict__ im = reinterpret_cast<const float4*>(p.feat) + sample + chunk * 4;
+  float4* __restrict__ ow =
+      p.out_warp ? reinterpret_cast<float4*>(p.out_warp) + sample + chunk * 4 : nullptr;
+  const int south = p.W * Cf4;
+#pragma unroll 1
+  for (int base = ptid; base < kItems; base += kProducerThreads * kUnroll) {
+    float4 a[kUnroll][4];
+    float4 w[kUnroll];
+    int gi[kUnroll], kcs[kUnroll];
+    uint32_t dst[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int item = base + u * kProducerThreads;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      a[u][0] = a[u][1] = a[u][2] = a[u][3] = z;
+      w[u] = z;
+      gi[u] = -1;
+      dst[u] = 0xffffffffu;
+      kcs[u] = 0;
+      if (item < kItems) {
+        const int q = item >> 2, kc = item & 3;
+        kcs[u] = kc;
+        dst[u] = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
+        gi[u] = s_gidx[q];
+        if (gi[u] >= 0) {
+          const unsigned pos = (unsigned)s_pos[q];
+          w[u] = s_wgt[q];
+          const float4* __restrict__ north = im + (pos & kOffMask) + kc;
+          const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
+          // ATen skips out-of-bounds taps (their weight is 0 anyway)
+          a[u][0] = ldg4(north);
+          if (e) a[u][1] = ldg4(north + Cf4);
+          if (sth) a[u][2] = ldg4(north + south);
+          if (e && sth) a[u][3] = ldg4(north + south + Cf4);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (dst[u] == 0xffffffffu) continue;
+      const float4 v = blend4(a[u][0], a[u][1], a[u][2], a[u][3], w[u]);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w)
+                   : "memory");
+      if (ow != nullptr && gi[u] >= 0 && (gi[u] & kInterior))
+        st_streaming(ow + (long long)(gi[u] & (kInterior - 1)) * Cf4 + kcs[u], v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+warp_conv3x3_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+  // barriers: full[2], empty[2], tmem_full[2], tmem_empty[2]
+  const uint32_t bar = s_base + kOffBar;
+  auto bar_full = [&](int s) { return bar + 8u * s; };
+  auto bar_empty = [&](int s) { return bar + 16u + 8u * s; };
+  auto bar_tfull = [&](int b) { return bar + 32u + 8u * b; };
+  auto bar_tempty = [&](int b) { return bar + 48u + 8u * b; };
+
+  if (threadIdx.x < kCo) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == kProducerWarps + kEpilogueWarps) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_full(s), kProducerWarps + 1);  // 8 producer warps + the weight loader
+        mbar_init(bar_empty(s), 1);                  // tcgen05.commit
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_tfull(b), 1);                  // tcgen05.commit
+        mbar_init(bar_tempty(b), kEpilogueWarps);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(s_tmem)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < kProducerWarps) {
+    // ===================== producers =====================
+    const int ptid = threadIdx.x;
+    float4* s_wgt = reinterpret_cast<float4*>(smem + kOffWgt);
+    int* s_pos = reinterpret_cast<int*>(smem + kOffPos);
+    int* s_gidx = reinterpret_cast<int*>(smem + kOffGidx);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const Tile t = tile_of(p, tile);
+      producer_bar();  // everyone is done with the previous tile's tap records
+      compute_taps(p, t, ptid, s_wgt, s_pos, s_gidx);
+      producer_bar();
+      for (int c = 0; c < p.n_chunks; ++c, ++it) {
+        const int s = it & 1;
+        mbar_wait(bar_empty(s), ((it >> 1) & 1) ^ 1);
+        const uint32_t a_stage = s_base + kOffA + s * kAStageBytes;
+        if (c < p.n_chunks_extra)
+          fill_extra(p, t, c, ptid, a_stage, s_gidx);
+        else
+          fill_warped(p, t, c - p.n_chunks_extra, ptid, a_stage, s_wgt, s_pos, s_gidx);
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full(s));
+      }
+    }
+  } else if (warp < kProducerWarps + kEpilogueWarps) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+      const Tile t = tile_of(p, tile);
+      const int buf = tl & 1;
+      mbar_wait(bar_tfull(buf), (tl >> 1) & 1);
+      tc_fence_after();
+      const int x = t.x0 + q * 32 + lane;
+#pragma unroll 1
+      for (int r = 0; r < kRows; ++r) {
+        const int y = t.y0 + r;
+        const bool ok = (y < p.H) && (x < p.W);
+        float4* __restrict__ o = reinterpret_cast<float4*>(p.out_conv) +
+                                 (((long long)t.n * p.H + y) * p.W + x) * (kCo / 4);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                 (uint32_t)(buf * (kRows * kCo) + r * kCo + half * 32);
+          tmem_ld32(taddr, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 f;
+              f.x = __uint_as_float(v[4 * j + 0]) + s_bias[half * 32 + 4 * j + 0];
+              f.y = __uint_as_float(v[4 * j + 1]) + s_bias[half * 32 + 4 * j + 1];
+              f.z = __uint_as_float(v[4 * j + 2]) + s_bias[half * 32 + 4 * j + 2];
+              f.w = __uint_as_float(v[4 * j + 3]) + s_bias[half * 32 + 4 * j + 3];
+              o[half * 8 + j] = f;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(buf));
+    }
+  } else if (warp == kProducerWarps + kEpilogueWarps) {
+    // ===================== MMA issuer =====================
+    uint32_t it = 0, tl = 0;
+    const uint32_t lbo_a = (p.debug & 1) ? 128u : (uint32_t)kPlanePix * 16u;
+    const uint32_t sbo_a = (p.debug & 1) ? (uint32_t)kPlanePix * 16u : 128u;
+    const uint32_t lbo_b = (p.debug & 1) ? 128u : (uint32_t)kCo * 16u;
+    const uint32_t sbo_b = (p.debug & 1) ? (uint32_t)kCo * 16u : 128u;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      mbar_wait(bar_tempty(buf), ((tl >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < p.n_chunks; ++c, ++it) {
+        const int s = it & 1;
+        mbar_wait(bar_full(s), (it >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t a0 = make_desc(s_base + kOffA + s * kAStageBytes, lbo_a, sbo_a);
+          const uint64_t b0 = make_desc(s_base + kOffB + s * kBStageBytes, lbo_b, sbo_b);
+#pragma unroll 1
+          for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              // descriptor start addresses advance in 16-byte units
+              const uint64_t bd = b0 + (uint64_t)((tap * 4 + ks * 2) * kCo);
+              const uint32_t acc = (c | ks | tap) != 0;
+#pragma unroll
+              for (int r = 0; r < kRows; ++r) {
+                const uint64_t ad =
+                    a0 + (uint64_t)(ks * 2 * kPlanePix + (r + dy) * kHaloW + dx);
+                tc_mma_tf32(tmem_base + (uint32_t)(buf * (kRows * kCo) + r * kCo), ad, bd,
+                            kIdesc, acc);
+              }
+            }
+          }
+          tc_commit(bar_empty(s));                       // stage free when these MMAs retire
+          if (c == p.n_chunks - 1) tc_commit(bar_tfull(buf));  // accumulators complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== weight loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < p.n_chunks; ++c, ++it) {
+          const int s = it & 1;
+          mbar_wait(bar_empty(s), ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full(s), kBStageBytes);
+          bulk_g2s(s_base + kOffB + s * kBStageBytes,
+                   reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kBStageBytes,
+                   kBStageBytes, bar_full(s));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps + kEpilogueWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// weight [Co=64, Ci, 3, 3] (element strides) -> [Ci/16][tap][k-chunk 4][co 64][4]
+__global__ void pack_weights_kernel(const float* __restrict__ w, long long s_co, long long s_ci,
+                                    long long s_ky, long long s_kx, float* __restrict__ out,
+                                    int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx & 3, co = (idx >> 2) & 63, kc = (idx >> 8) & 3;
+  const int rest = idx >> 10;
+  const int tap = rest % 9, cc = rest / 9;
+  const int ci = cc * kChunk + kc * 4 + j;
+  const int ky = tap / 3, kx = tap - ky * 3;
+  out[idx] = w[co * s_co + ci * s_ci + ky * s_ky + kx * s_kx];
+}
+
+}  // namespace wc
+}  // namespace dvc
+
+using namespace dvc;
+
+extern "C" int64_t dvc_conv3x3_packed_weight_floats(int64_t Co, int64_t Ci) {
+  if (Co != wc::kCo || Ci <= 0 || Ci % wc::kChunk) return 0;
+  return Ci * 9 * Co;
+}
+
+extern "C" int dvc_conv3x3_pack_weights(const float* weight, const int64_t w_st[4], int64_t Co,
+                                        int64_t Ci, float* packed, dvc_stream_t stream) {
+  DVC_REQUIRE(weight && packed && w_st, "conv3x3_pack_weights: null pointer");
+  DVC_REQUIRE(Co == wc::kCo, "conv3x3_pack_weights: Co must be 64 (got %lld)", (long long)Co);
+  DVC_REQUIRE(Ci > 0 && Ci % wc::kChunk == 0, "conv3x3_pack_weights: Ci must be a multiple of 16");
+  const int total = (int)(Ci * 9 * Co);
+  wc::pack_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      weight, w_st[0], w_st[1], w_st[2], w_st[3], packed, total);
+  return check_launch("pack_weights_kernel");
+}
+
+extern "C" int dvc_warp_conv3x3_fwd(const float* feat, const float* flow, const float* extra,
+                                    const float* packed_weight, const float* bias,
+                                    float* out_warp, float* out_conv, int64_t N, int64_t Cf,
+                                    int64_t Ce, int64_t Co, int64_t H, int64_t W,
+                                    const int64_t flow_st[4], int64_t flow_downscale, int flags,
+                                    dvc_stream_t stream) {
+  DVC_REQUIRE(feat && flow && packed_weight && out_conv && flow_st,
+              "warp_conv3x3: null pointer");
+  DVC_REQUIRE(N > 0 && H > 1 && W > 1, "warp_conv3x3: bad extents");
+  DVC_REQUIRE(Co == wc::kCo, "warp_conv3x3: Co must be 64 (got %lld)", (long long)Co);
+  DVC_REQUIRE(Cf > 0 && Cf % wc::kChunk == 0, "warp_conv3x3: Cf must be a multiple of 16");
+  DVC_REQUIRE(Ce >= 0 && Ce % wc::kChunk == 0, "warp_conv3x3: Ce must be a multiple of 16");
+  DVC_REQUIRE((Ce == 0) == (extra == nullptr), "warp_conv3x3: extra pointer / Ce mismatch");
+  DVC_REQUIRE(flow_downscale >= 0 && flow_downscale <= 2, "warp_conv3x3: flow_downscale in 0..2");
+  DVC_REQUIRE(aligned16(feat) && aligned16(extra) && aligned16(packed_weight) &&
+                  aligned16(out_warp) && aligned16(out_conv),
+              "warp_conv3x3: pointers must be 16-byte aligned");
+  DVC_REQUIRE((long double)H * W * (Cf > Ce ? Cf : Ce) / 4 < 1073741824.0L,
+              "warp_conv3x3: sample too large for 30-bit tap offsets");
+
+  wc::Params p;
+  p.feat = feat;
+  p.flow = flow;
+  p.extra = extra;
+  p.wpack = packed_weight;
+  p.bias = bias;
+  p.out_warp = out_warp;
+  p.out_conv = out_conv;
+  fill_geom(p.g, H, W, flags);
+  p.N = (int)N;
+  p.H = (int)H;
+  p.W = (int)W;
+  p.Cf = (int)Cf;
+  p.Ce = (int)Ce;
+  p.fl_n = flow_st[0];
+  p.fl_c = flow_st[1];
+  p.fl_h = flow_st[2];
+  p.fl_w = flow_st[3];
+  p.flow_level = (int)flow_downscale;
+  p.tiles_x = (int)((W + wc::kTileW - 1) / wc::kTileW);
+  p.tiles_y = (int)((H + wc::kRows - 1) / wc::kRows);
+  p.n_tiles = (int)(N * p.tiles_x * p.tiles_y);
+  p.n_chunks_extra = (int)(Ce / wc::kChunk);
+  p.n_chunks = (int)((Ce + Cf) / wc::kChunk);
+  p.debug = (flags >> 8) & 0xff;
+
+  cudaError_t e = cudaFuncSetAttribute(wc::warp_conv3x3_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       wc::kSmemBytes);
+  if (e != cudaSuccess)
+    return fail(DVC_ERR_CUDA, "warp_conv3x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  wc::warp_conv3x3_kernel<<<grid, wc::kThreads, wc::kSmemBytes, (cudaStream_t)stream>>>(p);
+  return check_launch("warp_conv3x3_kernel");
+}

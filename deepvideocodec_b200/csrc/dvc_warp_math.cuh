@@ -78,6 +78,48 @@ __device__ __forceinline__ float blend(float vnw, float vne, float vsw, float vs
   return acc;
 }
 
+// ---------------------------------------------------------------------------
+// flow fetch, optionally through the reference's flow pyramid
+//   level 1: bilineardownsacling(mv) / 2          (video_model.py:499)
+//   level 2: bilineardownsacling(level 1) / 2     (video_model.py:500)
+// evaluated per sample with exactly the arithmetic of flow_pyramid_kernel, so
+// warping with flow_level = k is bit-identical to warping with the
+// materialised mv2 / mv3.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float down2_at(const float* __restrict__ q, long long sh,
+                                          long long sw) {
+  const float a = __ldg(q), b = __ldg(q + sw);
+  const float c = __ldg(q + sh), d = __ldg(q + sh + sw);
+  return mul_rn(mul_rn(add_rn(add_rn(a, b), add_rn(c, d)), 0.25f), 0.5f);
+}
+
+__device__ __forceinline__ float fetch_flow(const float* __restrict__ plane, long long sh,
+                                            long long sw, int h, int w, int level) {
+  if (level == 0) return __ldg(plane + h * sh + w * sw);
+  if (level == 1) return down2_at(plane + (2 * h) * sh + (2 * w) * sw, sh, sw);
+  const float* q = plane + (4 * h) * sh + (4 * w) * sw;
+  const float m00 = down2_at(q, sh, sw), m01 = down2_at(q + 2 * sw, sh, sw);
+  const float m10 = down2_at(q + 2 * sh, sh, sw), m11 = down2_at(q + 2 * sh + 2 * sw, sh, sw);
+  return mul_rn(mul_rn(add_rn(add_rn(m00, m01), add_rn(m10, m11)), 0.25f), 0.5f);
+}
+
+// ---------------------------------------------------------------------------
+// float4 (4-channel group) helpers of the channels_last paths
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ float4 blend4(const float4& a, const float4& b, const float4& c,
+                                         const float4& d, const float4& w) {
+  float4 o;
+  o.x = fmaf(d.x, w.w, fmaf(c.x, w.z, fmaf(b.x, w.y, mul_rn(a.x, w.x))));
+  o.y = fmaf(d.y, w.w, fmaf(c.y, w.z, fmaf(b.y, w.y, mul_rn(a.y, w.x))));
+  o.z = fmaf(d.z, w.w, fmaf(c.z, w.z, fmaf(b.z, w.y, mul_rn(a.z, w.x))));
+  o.w = fmaf(d.w, w.w, fmaf(c.w, w.z, fmaf(b.w, w.y, mul_rn(a.w, w.x))));
+  return o;
+}
+
+constexpr unsigned kEastIn = 1u << 30, kSouthIn = 1u << 31, kOffMask = (1u << 30) - 1u;
+
 // host side: constants of the pipeline for an H x W image
 static inline int fill_geom(WarpGeom& g, int64_t H, int64_t W, int flags) {
   g.H = (int)H;

@@ -21,7 +21,7 @@ import torch
 from . import _native as nat
 
 __all__ = ["flow_warp", "torch_warp", "bilineardownsacling", "flow_pyramid",
-           "motion_compensation_warps"]
+           "motion_compensation_warps", "warp_conv3x3", "pack_conv3x3_weight"]
 
 
 def _check_warp_args(im, flow):
@@ -235,3 +235,95 @@ def motion_compensation_warps(x_ref, feat1, feat2, feat3, mv):
     # big task first so the small ones fill the tail of the grid
     c1, c2, c3, wf = warp_multi([(feat1, mv, 0), (feat2, mv, 1), (feat3, mv, 2), (x_ref, mv, 0)])
     return c1, c2, c3, wf
+
+
+# ---------------------------------------------------------------------------
+# warp fused into the 3x3 conv that consumes it (tcgen05)
+# ---------------------------------------------------------------------------
+_packed_weights = {}
+
+
+def pack_conv3x3_weight(weight):
+    """Re-lay a ``[64, Ci, 3, 3]`` conv weight into the UMMA operand layout.
+
+    Cached per (storage, version): re-packed only after the parameter changes.
+    """
+    nat.require_cuda_f32(weight, "pack_conv3x3_weight(weight)")
+    co, ci, kh, kw = weight.shape
+    if (kh, kw) != (3, 3):
+        raise nat.DvcError(f"pack_conv3x3_weight: 3x3 kernels only, got {kh}x{kw}")
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
+    hit = _packed_weights.get(weight.device.index)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    n = nat.lib().dvc_conv3x3_packed_weight_floats(co, ci)
+    if n <= 0:
+        raise nat.DvcError(f"pack_conv3x3_weight: need Co == 64 and Ci % 16 == 0, got {co}, {ci}")
+    packed = torch.empty(n, dtype=torch.float32, device=weight.device)
+    w = weight.detach()
+    with nat.device_of(w):
+        rc = nat.lib().dvc_conv3x3_pack_weights(w.data_ptr(), nat.st4(w), co, ci,
+                                                packed.data_ptr(), nat.stream_of(w))
+    nat.check(rc, "dvc_conv3x3_pack_weights")
+    _packed_weights[weight.device.index] = (key, packed)
+    return packed
+
+
+def _nhwc_dense(t):
+    return t if t.is_contiguous(memory_format=torch.channels_last) else \
+        t.contiguous(memory_format=torch.channels_last)
+
+
+def warp_conv3x3(feat, flow, weight, bias=None, extra=None, *, flow_downscale=0,
+                 want_warp=True, packed=None, _debug=0):
+    """``ctx = flow_warp(feat, flow)``; ``conv2d(cat((extra, ctx), 1), weight, bias, padding=1)``.
+
+    One tcgen05 implicit-GEMM kernel (TF32 operands, fp32 accumulation): the
+    warped tile goes from the gather straight into shared memory as the GEMM
+    operand and is written to HBM once, never re-read.  Replaces
+    ``flow_warp`` (layers.py:196) + ``conv{1,2,3}_out`` of
+    ``MultiScaleContextFusion`` (video_model.py:55-61).  Inference only.
+
+    Returns ``(ctx, conv)``, both channels_last; ``ctx`` is bit-identical to
+    :func:`flow_warp` (``None`` when ``want_warp`` is false).
+    """
+    nat.require_cuda_f32(feat, "warp_conv3x3(feat)")
+    nat.require_cuda_f32(flow, "warp_conv3x3(flow)")
+    nat.require_cuda_f32(weight, "warp_conv3x3(weight)")
+    n, cf, h, w = feat.shape
+    ce = 0
+    if extra is not None:
+        nat.require_cuda_f32(extra, "warp_conv3x3(extra)")
+        if extra.shape[0] != n or extra.shape[2:] != feat.shape[2:]:
+            raise nat.DvcError(f"warp_conv3x3: extra {tuple(extra.shape)} does not match feat "
+                               f"{tuple(feat.shape)}")
+        ce = extra.shape[1]
+        extra = _nhwc_dense(extra)
+    if flow.shape != (n, 2, h << flow_downscale, w << flow_downscale):
+        raise nat.DvcError(f"warp_conv3x3: flow must be [N,2,{h << flow_downscale},"
+                           f"{w << flow_downscale}], got {tuple(flow.shape)}")
+    co = weight.shape[0]
+    if weight.shape[1] != ce + cf:
+        raise nat.DvcError(f"warp_conv3x3: weight expects {weight.shape[1]} input channels, "
+                           f"got {ce} + {cf}")
+    if bias is not None and (not bias.is_cuda or bias.dtype != torch.float32 or
+                             bias.numel() != co or not bias.is_contiguous()):
+        raise nat.DvcError("warp_conv3x3: bias must be a contiguous CUDA fp32 [Co] tensor")
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                       for t in (feat, flow, extra, weight, bias)):
+        raise nat.DvcError("warp_conv3x3 is inference only (no backward); call it under "
+                           "torch.no_grad() or use flow_warp + conv2d for training")
+    feat = _nhwc_dense(feat)
+    if packed is None:
+        packed = pack_conv3x3_weight(weight)
+    ctx = torch.empty_like(feat) if want_warp else None
+    conv = torch.empty((n, co, h, w), dtype=torch.float32, device=feat.device,
+                       memory_format=torch.channels_last)
+    with nat.device_of(feat):
+        rc = nat.lib().dvc_warp_conv3x3_fwd(
+            feat.data_ptr(), flow.data_ptr(), nat.ptr(extra), packed.data_ptr(),
+            nat.ptr(None if bias is None else bias.detach()), nat.ptr(ctx), conv.data_ptr(),
+            n, cf, ce, co, h, w, nat.st4(flow), flow_downscale, (_debug & 0xff) << 8,
+            nat.stream_of(feat))
+    nat.check(rc, "dvc_warp_conv3x3_fwd")
+    return ctx, conv

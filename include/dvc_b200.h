@@ -121,6 +121,36 @@ int dvc_warp_multi_fwd(const dvc_warp_task* tasks /* HOST array */, int n_tasks,
                        int flags, dvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * warp fused into the 3x3 convolution that consumes it, as a
+ * tcgen05 (TF32, fp32 accumulate) implicit GEMM.  Replaces, for one scale,
+ *   context = flow_warp(ref_feature, mv)                    video_model.py:502-504
+ *   conv    = convK_out(torch.cat((up, context), dim=1))    video_model.py:55-61
+ * (nn.Conv2d(Ce + Cf, 64, 3, padding=1); `up` is `extra`, may be absent).
+ *   feat  [N,Cf,H,W]  channels_last DENSE (strides H*W*Cf, 1, W*Cf, Cf)
+ *   extra [N,Ce,H,W]  channels_last dense, [opt] (Ce = 0)
+ *   flow  [N,2,H<<k,W<<k] any strides, k = flow_downscale (see dvc_warp_task)
+ *   out_warp [N,Cf,H,W] channels_last dense, [opt]: bit-identical to
+ *            dvc_flow_warp_fwd;  out_conv [N,64,H,W] channels_last dense.
+ * Cf, Ce multiples of 16; Co = 64.  The weight [64, Ce+Cf, 3, 3] is re-laid
+ * once by dvc_conv3x3_pack_weights into dvc_conv3x3_packed_weight_floats()
+ * floats ([Ci/16][tap][ci%16/4][co][ci%4], the UMMA K-major operand layout).
+ * PyTorch's cuDNN convolutions run in TF32 by default; this kernel truncates
+ * the operands to TF32 in the tensor core and accumulates in fp32.
+ * ------------------------------------------------------------------------- */
+int64_t dvc_conv3x3_packed_weight_floats(int64_t Co, int64_t Ci);
+int dvc_conv3x3_pack_weights(const float* weight, const int64_t w_st[4],
+                             int64_t Co, int64_t Ci, float* packed,
+                             dvc_stream_t stream);
+int dvc_warp_conv3x3_fwd(const float* feat, const float* flow,
+                         const float* extra /*[opt]*/,
+                         const float* packed_weight, const float* bias /*[opt]*/,
+                         float* out_warp /*[opt]*/, float* out_conv, int64_t N,
+                         int64_t Cf, int64_t Ce, int64_t Co, int64_t H,
+                         int64_t W, const int64_t flow_st[4],
+                         int64_t flow_downscale, int flags,
+                         dvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Piece 2: quantisation.  quantize_ste forward, dmc/models/utils.py:149-152
  * (round half to even).  [opt] offset[C] implements the hyper-latent form
  * z_hat = round(z - med_c) + med_c (video_model.py:222-224); pass NULL for the
