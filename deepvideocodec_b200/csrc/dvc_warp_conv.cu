@@ -26,15 +26,19 @@
 // address advanced by ((r + dy) * 130 + dx) * 16 bytes -- no im2col copies.
 // The weights of the slice (9 taps x 16 ci x 64 co) arrive by one bulk copy.
 //
-// Warp roles (448 threads, persistent, one CTA per SM):
-//   warps 0-7  producers: tap records of the tile's halo (op-for-op replay of
-//              flow_warp), then per 16-channel slice either copy `extra` or
-//              gather + blend `feat` into the stage; interior pixels of the
-//              warped slice are also written to `out_warp`;
-//   warps 8-11 epilogue: TMEM -> registers -> + bias -> out_conv, overlapped
-//              with the next tile through the second TMEM accumulator set;
-//   warp 12    MMA issuer (one lane): 72 tcgen05.mma (M128 N64 K8) per slice;
-//   warp 13    weight loader (one lane): cp.async.bulk per slice.
+// Warp roles (640 threads, persistent, one CTA per SM):
+//   warps 0-13  producers: tap records of the tile's halo (op-for-op replay of
+//               flow_warp), then per 16-channel slice either copy `extra`
+//               (cp.async straight into the stage, completion reported to the
+//               stage's mbarrier, no register round trip and no wait) or
+//               gather + blend `feat` into the stage; interior pixels of the
+//               warped slice are also written to `out_warp`;
+//   warps 14-17 epilogue: TMEM -> registers -> + bias -> out_conv, overlapped
+//               with the next tile through the second TMEM accumulator set;
+//   warp 18     MMA issuer (one lane): 72 tcgen05.mma (M128 N64 K8) per slice;
+//   warp 19     weight loader (one lane): cp.async.bulk per slice.
+// 14 producer warps: 3120 work items per slice = 448 x 6 + 432, i.e. 7 items
+// per thread in two batches (4 + 3) of independent gathers.
 #include "dvc_common.cuh"
 #include "dvc_warp_math.cuh"
 
@@ -54,9 +58,9 @@ constexpr int kPlanePix = 786;
 constexpr int kAStageBytes = 4 * kPlanePix * 16;  // 50304
 constexpr int kBStageBytes = 9 * 4 * kCo * 16;    // 36864
 constexpr int kStages = 2;
-constexpr int kProducerWarps = 8, kEpilogueWarps = 4;
+constexpr int kProducerWarps = 14, kEpilogueWarps = 4;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 2) * 32;  // 448
+constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 2) * 32;  // 640
 constexpr int kTmemCols = 512;  // 2 sets x 4 accumulators x 64 columns
 
 // shared memory map (bytes)
@@ -238,28 +242,20 @@ __device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int c
   const int Ce4 = p.Ce >> 2;
   const float4* __restrict__ ex =
       reinterpret_cast<const float4*>(p.extra) + (long long)t.n * p.H * p.W * Ce4 + chunk * 4;
-#pragma unroll 1
-  for (int base = ptid; base < kItems; base += kProducerThreads * kUnroll) {
-    float4 v[kUnroll];
-    uint32_t dst[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int item = base + u * kProducerThreads;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      dst[u] = 0xffffffffu;
-      if (item < kItems) {
-        const int q = item >> 2, kc = item & 3;
-        dst[u] = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
-        const int gi = s_gidx[q];
-        if (gi >= 0) v[u] = ldg4(ex + (long long)(gi & (kInterior - 1)) * Ce4 + kc);
-      }
+  for (int k = 0; k < (kItems + kProducerThreads - 1) / kProducerThreads; ++k) {
+    const int item = ptid + k * kProducerThreads;
+    if (item < kItems) {
+      const int q = item >> 2, kc = item & 3;
+      const uint32_t dst = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
+      const int gi = s_gidx[q];
+      // outside the image: src-size 0 -> 16 bytes of zeros (the conv's zero padding)
+      const float4* src = ex + (gi >= 0 ? (long long)(gi & (kInterior - 1)) * Ce4 + kc : 0);
+      const uint32_t nbytes = gi >= 0 ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+                   "r"(nbytes)
+                   : "memory");
     }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (dst[u] != 0xffffffffu)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(v[u].x),
-                     "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
-                     : "memory");
   }
 }
 
@@ -275,26 +271,21 @@ __device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int 
 #pragma unroll 1
   for (int base = ptid; base < kItems; base += kProducerThreads * kUnroll) {
     float4 a[kUnroll][4];
-    float4 w[kUnroll];
-    int gi[kUnroll], kcs[kUnroll];
+    int gi[kUnroll];
     uint32_t dst[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int item = base + u * kProducerThreads;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       a[u][0] = a[u][1] = a[u][2] = a[u][3] = z;
-      w[u] = z;
       gi[u] = -1;
       dst[u] = 0xffffffffu;
-      kcs[u] = 0;
       if (item < kItems) {
         const int q = item >> 2, kc = item & 3;
-        kcs[u] = kc;
         dst[u] = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
         gi[u] = s_gidx[q];
         if (gi[u] >= 0) {
           const unsigned pos = (unsigned)s_pos[q];
-          w[u] = s_wgt[q];
           const float4* __restrict__ north = im + (pos & kOffMask) + kc;
           const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
           // ATen skips out-of-bounds taps (their weight is 0 anyway)
@@ -308,12 +299,13 @@ __device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int 
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (dst[u] == 0xffffffffu) continue;
-      const float4 v = blend4(a[u][0], a[u][1], a[u][2], a[u][3], w[u]);
+      const int item = base + u * kProducerThreads;
+      const float4 v = blend4(a[u][0], a[u][1], a[u][2], a[u][3], s_wgt[item >> 2]);
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(v.x), "f"(v.y),
                    "f"(v.z), "f"(v.w)
                    : "memory");
       if (ow != nullptr && gi[u] >= 0 && (gi[u] & kInterior))
-        st_streaming(ow + (long long)(gi[u] & (kInterior - 1)) * Cf4 + kcs[u], v);
+        st_streaming(ow + (long long)(gi[u] & (kInterior - 1)) * Cf4 + (item & 3), v);
     }
   }
 }
@@ -339,7 +331,7 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
   if (warp == kProducerWarps + kEpilogueWarps) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
-        mbar_init(bar_full(s), kProducerWarps + 1);  // 8 producer warps + the weight loader
+        mbar_init(bar_full(s), kProducerThreads + 1);  // producer threads + the weight loader
         mbar_init(bar_empty(s), 1);                  // tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -376,13 +368,16 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
         const int s = it & 1;
         mbar_wait(bar_empty(s), ((it >> 1) & 1) ^ 1);
         const uint32_t a_stage = s_base + kOffA + s * kAStageBytes;
-        if (c < p.n_chunks_extra)
+        if (c < p.n_chunks_extra) {
           fill_extra(p, t, c, ptid, a_stage, s_gidx);
-        else
+          // arrive when this thread's copies have landed; the thread moves on
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full(s))
+                       : "memory");
+        } else {
           fill_warped(p, t, c - p.n_chunks_extra, ptid, a_stage, s_wgt, s_pos, s_gidx);
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full(s));
+          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+          mbar_arrive(bar_full(s));
+        }
       }
     }
   } else if (warp < kProducerWarps + kEpilogueWarps) {
