@@ -75,6 +75,7 @@ constexpr int kOffTmem = kOffBar + 8 * 8;                 // uint32
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffWgt % 16 == 0 && kOffB % 16 == 0, "smem alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kProducerThreads % 4 == 0, "a thread keeps one k-chunk");
 
 constexpr int kInterior = 1 << 30;  // gidx flag: the CTA owns this pixel of out_warp
 
@@ -117,10 +118,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)   // may sleep up to 20 us; woken by the phase flip
       : "memory");
   return ok != 0;
 }
@@ -129,7 +130,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -163,6 +164,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+// One lane of a converged warp; the compiler knows the guarded region is
+// single-threaded, so tcgen05 operands stay in uniform registers without a
+// per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void producer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
@@ -235,25 +248,49 @@ __device__ __forceinline__ void compute_taps(const Params& p, const Tile& t, int
 }
 
 constexpr int kItems = kHaloPix * 4;  // (halo pixel, 4-channel k-chunk) work items per slice
-constexpr int kUnroll = 4;
+constexpr int kItemsPerThread = (kItems + kProducerThreads - 1) / kProducerThreads;  // 7
+constexpr int kBatch = 4;             // independent gathers in flight per thread: 4 items x 4 taps
+
+// The (pixel, k-chunk) items of a thread are the same for every slice of a tile:
+// item k of thread t is t + k * 448.  Its tap record is read from shared memory
+// once per tile and kept in registers, so the load phase of a slice is pure
+// address arithmetic + LDG (no LDS -> no short-scoreboard stalls before the gathers).
+struct Items {
+  int pos[kItemsPerThread];   // float4 offset of the nw tap | kEastIn | kSouthIn
+  int gi[kItemsPerThread];    // pixel index | kInterior, or -1 outside the image / no item
+};
+
+__device__ __forceinline__ void load_items(Items& it, int ptid, const int* s_pos,
+                                           const int* s_gidx) {
+#pragma unroll
+  for (int k = 0; k < kItemsPerThread; ++k) {
+    const int item = ptid + k * kProducerThreads;
+    const int q = (item < kItems ? item : 0) >> 2;
+    it.pos[k] = s_pos[q];
+    it.gi[k] = item < kItems ? s_gidx[q] : -1;
+  }
+}
+
+__device__ __forceinline__ uint32_t item_dst(uint32_t a_stage, int ptid, int k) {
+  const int item = ptid + k * kProducerThreads;
+  return a_stage + (uint32_t)((item & 3) * kPlanePix + (item >> 2)) * 16u;
+}
 
 __device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int chunk, int ptid,
-                                           uint32_t a_stage, const int* s_gidx) {
+                                           uint32_t a_stage, const Items& it) {
   const int Ce4 = p.Ce >> 2;
-  const float4* __restrict__ ex =
-      reinterpret_cast<const float4*>(p.extra) + (long long)t.n * p.H * p.W * Ce4 + chunk * 4;
+  const float4* __restrict__ ex = reinterpret_cast<const float4*>(p.extra) +
+                                  (long long)t.n * p.H * p.W * Ce4 + chunk * 4 + (ptid & 3);
 #pragma unroll
-  for (int k = 0; k < (kItems + kProducerThreads - 1) / kProducerThreads; ++k) {
-    const int item = ptid + k * kProducerThreads;
-    if (item < kItems) {
-      const int q = item >> 2, kc = item & 3;
-      const uint32_t dst = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
-      const int gi = s_gidx[q];
+  for (int k = 0; k < kItemsPerThread; ++k) {
+    if (ptid + k * kProducerThreads < kItems) {
+      const int gi = it.gi[k];
       // outside the image: src-size 0 -> 16 bytes of zeros (the conv's zero padding)
-      const float4* src = ex + (gi >= 0 ? (long long)(gi & (kInterior - 1)) * Ce4 + kc : 0);
+      const float4* src = ex + (gi >= 0 ? (long long)(gi & (kInterior - 1)) * Ce4 : 0);
       const uint32_t nbytes = gi >= 0 ? 16u : 0u;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
-                   "r"(nbytes)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                       item_dst(a_stage, ptid, k)),
+                   "l"(src), "r"(nbytes)
                    : "memory");
     }
   }
@@ -261,51 +298,48 @@ __device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int c
 
 __device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int chunk, int ptid,
                                             uint32_t a_stage, const float4* s_wgt,
-                                            const int* s_pos, const int* s_gidx) {
+                                            const Items& it) {
   const int Cf4 = p.Cf >> 2;
   const long long sample = (long long)t.n * p.H * p.W * Cf4;
-  const float4* __restrict__ im = reinterpret_cast<const float4*>(p.feat) + sample + chunk * 4;
+  // kProducerThreads % 4 == 0: the k-chunk of every item of this thread is ptid & 3
+  const float4* __restrict__ im =
+      reinterpret_cast<const float4*>(p.feat) + sample + chunk * 4 + (ptid & 3);
   float4* __restrict__ ow =
-      p.out_warp ? reinterpret_cast<float4*>(p.out_warp) + sample + chunk * 4 : nullptr;
+      p.out_warp ? reinterpret_cast<float4*>(p.out_warp) + sample + chunk * 4 + (ptid & 3)
+                 : nullptr;
   const int south = p.W * Cf4;
-#pragma unroll 1
-  for (int base = ptid; base < kItems; base += kProducerThreads * kUnroll) {
-    float4 a[kUnroll][4];
-    int gi[kUnroll];
-    uint32_t dst[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int item = base + u * kProducerThreads;
+  for (int k0 = 0; k0 < kItemsPerThread; k0 += kBatch) {
+    float4 a[kBatch][4];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int k = k0 + u;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       a[u][0] = a[u][1] = a[u][2] = a[u][3] = z;
-      gi[u] = -1;
-      dst[u] = 0xffffffffu;
-      if (item < kItems) {
-        const int q = item >> 2, kc = item & 3;
-        dst[u] = a_stage + (uint32_t)(kc * kPlanePix + q) * 16u;
-        gi[u] = s_gidx[q];
-        if (gi[u] >= 0) {
-          const unsigned pos = (unsigned)s_pos[q];
-          const float4* __restrict__ north = im + (pos & kOffMask) + kc;
-          const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
-          // ATen skips out-of-bounds taps (their weight is 0 anyway)
-          a[u][0] = ldg4(north);
-          if (e) a[u][1] = ldg4(north + Cf4);
-          if (sth) a[u][2] = ldg4(north + south);
-          if (e && sth) a[u][3] = ldg4(north + south + Cf4);
-        }
+      if (k < kItemsPerThread && it.gi[k] >= 0) {
+        const unsigned pos = (unsigned)it.pos[k];
+        const float4* __restrict__ north = im + (pos & kOffMask);
+        const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
+        // ATen skips out-of-bounds taps (their weight is 0 anyway)
+        a[u][0] = ldg4(north);
+        if (e) a[u][1] = ldg4(north + Cf4);
+        if (sth) a[u][2] = ldg4(north + south);
+        if (e && sth) a[u][3] = ldg4(north + south + Cf4);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (dst[u] == 0xffffffffu) continue;
-      const int item = base + u * kProducerThreads;
+    for (int u = 0; u < kBatch; ++u) {
+      const int k = k0 + u;
+      if (k >= kItemsPerThread) continue;
+      const int item = ptid + k * kProducerThreads;
+      if (item >= kItems) continue;
       const float4 v = blend4(a[u][0], a[u][1], a[u][2], a[u][3], s_wgt[item >> 2]);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(v.x), "f"(v.y),
-                   "f"(v.z), "f"(v.w)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(item_dst(a_stage, ptid, k)),
+                   "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                    : "memory");
-      if (ow != nullptr && gi[u] >= 0 && (gi[u] & kInterior))
-        st_streaming(ow + (long long)(gi[u] & (kInterior - 1)) * Cf4 + (item & 3), v);
+      const int gi = it.gi[k];
+      if (ow != nullptr && gi >= 0 && (gi & kInterior))
+        st_streaming(ow + (long long)(gi & (kInterior - 1)) * Cf4, v);
     }
   }
 }
@@ -364,17 +398,19 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
       producer_bar();  // everyone is done with the previous tile's tap records
       compute_taps(p, t, ptid, s_wgt, s_pos, s_gidx);
       producer_bar();
+      Items items;
+      load_items(items, ptid, s_pos, s_gidx);
       for (int c = 0; c < p.n_chunks; ++c, ++it) {
         const int s = it & 1;
         mbar_wait(bar_empty(s), ((it >> 1) & 1) ^ 1);
         const uint32_t a_stage = s_base + kOffA + s * kAStageBytes;
         if (c < p.n_chunks_extra) {
-          fill_extra(p, t, c, ptid, a_stage, s_gidx);
+          fill_extra(p, t, c, ptid, a_stage, items);
           // arrive when this thread's copies have landed; the thread moves on
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full(s))
                        : "memory");
         } else {
-          fill_warped(p, t, c - p.n_chunks_extra, ptid, a_stage, s_wgt, s_pos, s_gidx);
+          fill_warped(p, t, c - p.n_chunks_extra, ptid, a_stage, s_wgt, items);
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
           mbar_arrive(bar_full(s));
         }
@@ -435,23 +471,23 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
         const int s = it & 1;
         mbar_wait(bar_full(s), (it >> 1) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint64_t a0 = make_desc(s_base + kOffA + s * kAStageBytes, lbo_a, sbo_a);
           const uint64_t b0 = make_desc(s_base + kOffB + s * kBStageBytes, lbo_b, sbo_b);
-#pragma unroll 1
+          const uint32_t d0 = tmem_base + (uint32_t)(buf * (kRows * kCo));
+#pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll 1
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int dy = tap / 3, dx = tap - dy * 3;
               // descriptor start addresses advance in 16-byte units
               const uint64_t bd = b0 + (uint64_t)((tap * 4 + ks * 2) * kCo);
-              const uint32_t acc = (c | ks | tap) != 0;
+              const uint32_t acc = (ks | tap) != 0 ? 1u : (uint32_t)(c != 0);
 #pragma unroll
               for (int r = 0; r < kRows; ++r) {
                 const uint64_t ad =
                     a0 + (uint64_t)(ks * 2 * kPlanePix + (r + dy) * kHaloW + dx);
-                tc_mma_tf32(tmem_base + (uint32_t)(buf * (kRows * kCo) + r * kCo), ad, bd,
-                            kIdesc, acc);
+                tc_mma_tf32(d0 + (uint32_t)(r * kCo), ad, bd, kIdesc, acc);
               }
             }
           }
