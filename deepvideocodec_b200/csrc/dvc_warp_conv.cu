@@ -26,19 +26,22 @@
 // address advanced by ((r + dy) * 130 + dx) * 16 bytes -- no im2col copies.
 // The weights of the slice (9 taps x 16 ci x 64 co) arrive by one bulk copy.
 //
-// Warp roles (640 threads, persistent, one CTA per SM):
-//   warps 0-13  producers: tap records of the tile's halo (op-for-op replay of
+// Warp roles (736 threads, persistent, one CTA per SM):
+//   warps 0-16  producers: tap records of the tile's halo (op-for-op replay of
 //               flow_warp), then per 16-channel slice either copy `extra`
 //               (cp.async straight into the stage, completion reported to the
 //               stage's mbarrier, no register round trip and no wait) or
 //               gather + blend `feat` into the stage; interior pixels of the
 //               warped slice are also written to `out_warp`;
-//   warps 14-17 epilogue: TMEM -> registers -> + bias -> out_conv, overlapped
+//   warps 17-20 epilogue: TMEM -> registers -> + bias -> out_conv, overlapped
 //               with the next tile through the second TMEM accumulator set;
-//   warp 18     MMA issuer (one lane): 72 tcgen05.mma (M128 N64 K8) per slice;
-//   warp 19     weight loader (one lane): cp.async.bulk per slice.
-// 14 producer warps: 3120 work items per slice = 448 x 6 + 432, i.e. 7 items
-// per thread in two batches (4 + 3) of independent gathers.
+//   warp 21     MMA issuer (one lane): 72 tcgen05.mma (M128 N64 K8) per slice;
+//   warp 22     weight loader (one lane): cp.async.bulk per slice.
+// A producer thread owns one (halo column, 4-channel k-chunk) pair and walks
+// the 6 halo rows in two batches of 3 vertically adjacent pixels: the south
+// taps of a row are the north taps of the next one, so back-to-back gathers of
+// one warp share their sectors in L1 (the kernel sits at the L2-throughput
+// ceiling, not at HBM's: every L1 hit is L2 bandwidth returned to the GEMM).
 #include "dvc_common.cuh"
 #include "dvc_warp_math.cuh"
 
@@ -58,9 +61,9 @@ constexpr int kPlanePix = 786;
 constexpr int kAStageBytes = 4 * kPlanePix * 16;  // 50304
 constexpr int kBStageBytes = 9 * 4 * kCo * 16;    // 36864
 constexpr int kStages = 2;
-constexpr int kProducerWarps = 14, kEpilogueWarps = 4;
+constexpr int kProducerWarps = 17, kEpilogueWarps = 4;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 2) * 32;  // 640
+constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 2) * 32;  // 736
 constexpr int kTmemCols = 512;  // 2 sets x 4 accumulators x 64 columns
 
 // shared memory map (bytes)
@@ -75,7 +78,6 @@ constexpr int kOffTmem = kOffBar + 8 * 8;                 // uint32
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffWgt % 16 == 0 && kOffB % 16 == 0, "smem alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-static_assert(kProducerThreads % 4 == 0, "a thread keeps one k-chunk");
 
 constexpr int kInterior = 1 << 30;  // gidx flag: the CTA owns this pixel of out_warp
 
@@ -247,61 +249,59 @@ __device__ __forceinline__ void compute_taps(const Params& p, const Tile& t, int
   }
 }
 
-constexpr int kItems = kHaloPix * 4;  // (halo pixel, 4-channel k-chunk) work items per slice
-constexpr int kItemsPerThread = (kItems + kProducerThreads - 1) / kProducerThreads;  // 7
-constexpr int kBatch = 4;             // independent gathers in flight per thread: 4 items x 4 taps
+// A producer thread owns the pair (halo column, k-chunk) = (ptid >> 2, ptid & 3)
+// and the 6 halo pixels of that column; 130 x 4 = 520 of the 544 threads work.
+constexpr int kFillThreads = kHaloW * 4;
+constexpr int kBatch = 3;   // vertically adjacent pixels gathered together (12 LDG.128 in flight)
+static_assert(kFillThreads <= kProducerThreads && kHaloH % kBatch == 0, "producer mapping");
 
-// The (pixel, k-chunk) items of a thread are the same for every slice of a tile:
-// item k of thread t is t + k * 448.  Its tap record is read from shared memory
-// once per tile and kept in registers, so the load phase of a slice is pure
-// address arithmetic + LDG (no LDS -> no short-scoreboard stalls before the gathers).
+// The tap records of a thread's 6 pixels are read from shared memory once per
+// tile and kept in registers: the load phase of a slice is address arithmetic
+// + LDG only.
 struct Items {
-  int pos[kItemsPerThread];   // float4 offset of the nw tap | kEastIn | kSouthIn
-  int gi[kItemsPerThread];    // pixel index | kInterior, or -1 outside the image / no item
+  int pos[kHaloH];   // float4 offset of the nw tap | kEastIn | kSouthIn
+  int gi[kHaloH];    // pixel index | kInterior, or -1 outside the image / idle thread
 };
 
 __device__ __forceinline__ void load_items(Items& it, int ptid, const int* s_pos,
                                            const int* s_gidx) {
+  const int col = ptid < kFillThreads ? (ptid >> 2) : 0;
 #pragma unroll
-  for (int k = 0; k < kItemsPerThread; ++k) {
-    const int item = ptid + k * kProducerThreads;
-    const int q = (item < kItems ? item : 0) >> 2;
-    it.pos[k] = s_pos[q];
-    it.gi[k] = item < kItems ? s_gidx[q] : -1;
+  for (int r = 0; r < kHaloH; ++r) {
+    it.pos[r] = s_pos[r * kHaloW + col];
+    it.gi[r] = ptid < kFillThreads ? s_gidx[r * kHaloW + col] : -1;
   }
 }
 
-__device__ __forceinline__ uint32_t item_dst(uint32_t a_stage, int ptid, int k) {
-  const int item = ptid + k * kProducerThreads;
-  return a_stage + (uint32_t)((item & 3) * kPlanePix + (item >> 2)) * 16u;
+__device__ __forceinline__ uint32_t item_dst(uint32_t a_stage, int ptid, int r) {
+  return a_stage + (uint32_t)((ptid & 3) * kPlanePix + r * kHaloW + (ptid >> 2)) * 16u;
 }
 
 __device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int chunk, int ptid,
                                            uint32_t a_stage, const Items& it) {
+  if (ptid >= kFillThreads) return;
   const int Ce4 = p.Ce >> 2;
   const float4* __restrict__ ex = reinterpret_cast<const float4*>(p.extra) +
                                   (long long)t.n * p.H * p.W * Ce4 + chunk * 4 + (ptid & 3);
 #pragma unroll
-  for (int k = 0; k < kItemsPerThread; ++k) {
-    if (ptid + k * kProducerThreads < kItems) {
-      const int gi = it.gi[k];
-      // outside the image: src-size 0 -> 16 bytes of zeros (the conv's zero padding)
-      const float4* src = ex + (gi >= 0 ? (long long)(gi & (kInterior - 1)) * Ce4 : 0);
-      const uint32_t nbytes = gi >= 0 ? 16u : 0u;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                       item_dst(a_stage, ptid, k)),
-                   "l"(src), "r"(nbytes)
-                   : "memory");
-    }
+  for (int r = 0; r < kHaloH; ++r) {
+    const int gi = it.gi[r];
+    // outside the image: src-size 0 -> 16 bytes of zeros (the conv's zero padding)
+    const float4* src = ex + (gi >= 0 ? (long long)(gi & (kInterior - 1)) * Ce4 : 0);
+    const uint32_t nbytes = gi >= 0 ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                     item_dst(a_stage, ptid, r)),
+                 "l"(src), "r"(nbytes)
+                 : "memory");
   }
 }
 
 __device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int chunk, int ptid,
                                             uint32_t a_stage, const float4* s_wgt,
                                             const Items& it) {
+  if (ptid >= kFillThreads) return;
   const int Cf4 = p.Cf >> 2;
   const long long sample = (long long)t.n * p.H * p.W * Cf4;
-  // kProducerThreads % 4 == 0: the k-chunk of every item of this thread is ptid & 3
   const float4* __restrict__ im =
       reinterpret_cast<const float4*>(p.feat) + sample + chunk * 4 + (ptid & 3);
   float4* __restrict__ ow =
@@ -309,15 +309,14 @@ __device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int 
                  : nullptr;
   const int south = p.W * Cf4;
 #pragma unroll
-  for (int k0 = 0; k0 < kItemsPerThread; k0 += kBatch) {
+  for (int r0 = 0; r0 < kHaloH; r0 += kBatch) {
     float4 a[kBatch][4];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
-      const int k = k0 + u;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       a[u][0] = a[u][1] = a[u][2] = a[u][3] = z;
-      if (k < kItemsPerThread && it.gi[k] >= 0) {
-        const unsigned pos = (unsigned)it.pos[k];
+      if (it.gi[r0 + u] >= 0) {
+        const unsigned pos = (unsigned)it.pos[r0 + u];
         const float4* __restrict__ north = im + (pos & kOffMask);
         const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
         // ATen skips out-of-bounds taps (their weight is 0 anyway)
@@ -329,15 +328,13 @@ __device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int 
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
-      const int k = k0 + u;
-      if (k >= kItemsPerThread) continue;
-      const int item = ptid + k * kProducerThreads;
-      if (item >= kItems) continue;
-      const float4 v = blend4(a[u][0], a[u][1], a[u][2], a[u][3], s_wgt[item >> 2]);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(item_dst(a_stage, ptid, k)),
+      const int r = r0 + u;
+      const float4 v =
+          blend4(a[u][0], a[u][1], a[u][2], a[u][3], s_wgt[r * kHaloW + (ptid >> 2)]);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(item_dst(a_stage, ptid, r)),
                    "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                    : "memory");
-      const int gi = it.gi[k];
+      const int gi = it.gi[r];
       if (ow != nullptr && gi >= 0 && (gi & kInterior))
         st_streaming(ow + (long long)(gi & (kInterior - 1)) * Cf4, v);
     }
@@ -440,14 +437,19 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
           tmem_ld32(taddr, v);
           tmem_ld_wait();
           if (ok) {
+            // one 256-bit store per lane = one full 32-byte sector per request
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 f;
-              f.x = __uint_as_float(v[4 * j + 0]) + s_bias[half * 32 + 4 * j + 0];
-              f.y = __uint_as_float(v[4 * j + 1]) + s_bias[half * 32 + 4 * j + 1];
-              f.z = __uint_as_float(v[4 * j + 2]) + s_bias[half * 32 + 4 * j + 2];
-              f.w = __uint_as_float(v[4 * j + 3]) + s_bias[half * 32 + 4 * j + 3];
-              o[half * 8 + j] = f;
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                f[e] = __uint_as_float(v[8 * j + e]) + s_bias[half * 32 + 8 * j + e];
+              asm volatile(
+                  "st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(
+                      o + half * 8 + 2 * j),
+                  "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]),
+                  "f"(f[7])
+                  : "memory");
             }
           }
         }
