@@ -15,8 +15,10 @@ from . import coder  # noqa: F401
 from .entropy_models import (EntropyBottleneck, EntropyModel, GaussianConditional,  # noqa: F401
                              LowerBound)
 from .layers import (bilineardownsacling, flow_pyramid, flow_warp,  # noqa: F401
-                     motion_compensation_warps, torch_warp, warp_multi)
-from .patch import install_compressai_shim, patch, unpatch  # noqa: F401
+                     motion_compensation_warps, pack_conv3x3_weight, torch_warp, warp_conv3x3,
+                     warp_multi)
+from .patch import (install_compressai_shim, motion_compensation_fused, patch,  # noqa: F401
+                    unpatch)
 from .rate import collect_likelihoods_list, frame_bits, log_sum, rate_finalize  # noqa: F401
 from .utils import quantize_around, quantize_ste  # noqa: F401
 

@@ -13,7 +13,7 @@ import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
-LIB_PATH = os.path.join(_PKG_DIR, "libdvc_b200.so")
+LIB_PATH = os.environ.get("DVC_B200_LIB") or os.path.join(_PKG_DIR, "libdvc_b200.so")   # override: A/B kernel builds
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(_REPO_DIR, "include")
 SOURCES = ("dvc_api.cu", "dvc_warp.cu", "dvc_warp_bwd.cu", "dvc_entropy.cu", "dvc_entropy_bwd.cu",
@@ -72,7 +72,7 @@ _SIGNATURES = {
     "dvc_flow_pyramid_fwd": (c_int, [c_void_p] * 3 + [c_int64] * 3 + [_P4] * 3 + [c_void_p]),
     "dvc_warp_multi_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dvc_conv3x3_packed_weight_floats": (c_int64, [c_int64] * 2),
-    "dvc_conv3x3_pack_weights": (c_int, [c_void_p, _P4, c_int64, c_int64, c_void_p, c_void_p]),
+    "dvc_conv3x3_pack_weights": (c_int, [c_void_p, _P4, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "dvc_warp_conv3x3_fwd": (c_int, [c_void_p] * 7 + [c_int64] * 6 + [_P4, c_int64, c_int, c_void_p]),
     "dvc_quantize_fwd": (c_int, [c_void_p] * 3 + [c_int64] * 4 + [_P4, c_int64, _P4, c_void_p]),
     "dvc_dual_prior_stage_a_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [_P4] * 4 + [c_void_p]),

@@ -24,7 +24,7 @@
 // consecutive pixels are one 128-byte core matrix, so the operand view of tap
 // (dy, dx) for output row r is the SAME buffer with the descriptor start
 // address advanced by ((r + dy) * 130 + dx) * 16 bytes -- no im2col copies.
-// The weights of the slice (9 taps x 16 ci x 64 co) arrive by one bulk copy.
+// The weights of a K = 8 step (9 taps x 8 ci x 64 co, 18 KB) arrive by one bulk copy.
 //
 // Warp roles (736 threads, persistent, one CTA per SM):
 //   warps 0-16  producers: tap records of the tile's halo (op-for-op replay of
@@ -36,12 +36,12 @@
 //   warps 17-20 epilogue: TMEM -> registers -> + bias -> out_conv, overlapped
 //               with the next tile through the second TMEM accumulator set;
 //   warp 21     MMA issuer (one lane): 72 tcgen05.mma (M128 N64 K8) per slice;
-//   warp 22     weight loader (one lane): cp.async.bulk per slice.
+//   warp 22     weight loader (one lane): one cp.async.bulk per K-step.
 // A producer thread owns one (halo column, 4-channel k-chunk) pair and walks
 // the 6 halo rows in two batches of 3 vertically adjacent pixels: the south
 // taps of a row are the north taps of the next one, so back-to-back gathers of
-// one warp share their sectors in L1 (the kernel sits at the L2-throughput
-// ceiling, not at HBM's: every L1 hit is L2 bandwidth returned to the GEMM).
+// one warp can share their sectors in L1 (ncu: the kernel moves ~7 GB through L2
+// for 2.1 GB of HBM traffic -- L2/L1 bandwidth, not HBM, is what the gathers cost).
 #include "dvc_common.cuh"
 #include "dvc_warp_math.cuh"
 
@@ -59,8 +59,22 @@ constexpr int kHaloPix = kHaloW * kHaloH;  // 780
 // lanes of two neighbouring pixels (one 8-lane store phase) hit 32 distinct banks
 constexpr int kPlanePix = 786;
 constexpr int kAStageBytes = 4 * kPlanePix * 16;  // 50304
-constexpr int kBStageBytes = 9 * 4 * kCo * 16;    // 36864
-constexpr int kStages = 2;
+constexpr int kBStageBytes = 9 * 2 * kCo * 16;    // 18432: the weights of ONE K = 8 step
+// Pipeline shape, measured on B200 at 1080p (us; profiles/r01_warp_conv.md):
+//   A x B stages, interleave:  2x2,0: 835   2x3,0: 857   2x3,1: 893   3x3,0: 980   3x3,1: 1005
+// Deeper is SLOWER: the gathers live off the L1 that shared memory leaves over
+// (156 KB of stages -> 92 KB of L1; 220 KB -> 28 KB), and two A stages cannot
+// average a cheap `extra` slice with an expensive warped one anyway.
+#ifndef WC_STAGES_A
+#define WC_STAGES_A 2
+#endif
+#ifndef WC_STAGES_B
+#define WC_STAGES_B 2
+#endif
+#ifndef WC_INTERLEAVE
+#define WC_INTERLEAVE 0
+#endif
+constexpr int kStagesA = WC_STAGES_A, kStagesB = WC_STAGES_B;
 constexpr int kProducerWarps = 17, kEpilogueWarps = 4;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = (kProducerWarps + kEpilogueWarps + 2) * 32;  // 736
@@ -68,13 +82,14 @@ constexpr int kTmemCols = 512;  // 2 sets x 4 accumulators x 64 columns
 
 // shared memory map (bytes)
 constexpr int kOffA = 0;
-constexpr int kOffB = kOffA + kStages * kAStageBytes;
-constexpr int kOffWgt = kOffB + kStages * kBStageBytes;   // float4[780]
+constexpr int kOffB = kOffA + kStagesA * kAStageBytes;
+constexpr int kOffWgt = kOffB + kStagesB * kBStageBytes;  // float4[780]
 constexpr int kOffPos = kOffWgt + kHaloPix * 16;          // int[780]
 constexpr int kOffGidx = kOffPos + kHaloPix * 4;          // int[780]
 constexpr int kOffBias = kOffGidx + kHaloPix * 4;         // float[64]
-constexpr int kOffBar = kOffBias + kCo * 4;               // uint64[8]
-constexpr int kOffTmem = kOffBar + 8 * 8;                 // uint32
+constexpr int kNumBars = 2 * kStagesA + 2 * kStagesB + 4;
+constexpr int kOffBar = kOffBias + kCo * 4;               // uint64[kNumBars]
+constexpr int kOffTmem = kOffBar + kNumBars * 8;          // uint32
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kOffBar % 8 == 0 && kOffWgt % 16 == 0 && kOffB % 16 == 0, "smem alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -101,6 +116,23 @@ struct Params {
   int n_chunks_extra, n_chunks;
   int debug;
 };
+
+// Order in which the 16-channel slices are consumed: all `extra` slices, then
+// all warped ones (WC_INTERLEAVE = 1 alternates them; measured slower, see
+// above).  Returns the slice index within its tensor.
+__host__ __device__ inline int slice_of(int c, int n_extra, int n_feat, bool* is_extra) {
+  const int m = WC_INTERLEAVE ? (n_extra < n_feat ? n_extra : n_feat) : 0;
+  if (!WC_INTERLEAVE) {
+    *is_extra = c < n_extra;
+    return c < n_extra ? c : c - n_extra;
+  }
+  if (c < 2 * m) {
+    *is_extra = (c & 1) == 0;
+    return c >> 1;
+  }
+  *is_extra = n_extra > n_feat;
+  return m + (c - 2 * m);
+}
 
 // ---- PTX wrappers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -351,19 +383,25 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
   const uint32_t s_base = smem_u32(smem);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
-  // barriers: full[2], empty[2], tmem_full[2], tmem_empty[2]
+  // barriers: fullA[3], emptyA[3], fullB[3], emptyB[3], tmem_full[2], tmem_empty[2]
   const uint32_t bar = s_base + kOffBar;
-  auto bar_full = [&](int s) { return bar + 8u * s; };
-  auto bar_empty = [&](int s) { return bar + 16u + 8u * s; };
-  auto bar_tfull = [&](int b) { return bar + 32u + 8u * b; };
-  auto bar_tempty = [&](int b) { return bar + 48u + 8u * b; };
+  auto bar_full_a = [&](int s) { return bar + 8u * s; };
+  auto bar_empty_a = [&](int s) { return bar + 8u * (kStagesA + s); };
+  auto bar_full_b = [&](int s) { return bar + 8u * (2 * kStagesA + s); };
+  auto bar_empty_b = [&](int s) { return bar + 8u * (2 * kStagesA + kStagesB + s); };
+  auto bar_tfull = [&](int b) { return bar + 8u * (2 * kStagesA + 2 * kStagesB + b); };
+  auto bar_tempty = [&](int b) { return bar + 8u * (2 * kStagesA + 2 * kStagesB + 2 + b); };
 
   if (threadIdx.x < kCo) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (warp == kProducerWarps + kEpilogueWarps) {
     if (lane == 0) {
-      for (int s = 0; s < kStages; ++s) {
-        mbar_init(bar_full(s), kProducerThreads + 1);  // producer threads + the weight loader
-        mbar_init(bar_empty(s), 1);                  // tcgen05.commit
+      for (int s = 0; s < kStagesA; ++s) {
+        mbar_init(bar_full_a(s), kProducerThreads);
+        mbar_init(bar_empty_a(s), 1);                // tcgen05.commit
+      }
+      for (int s = 0; s < kStagesB; ++s) {
+        mbar_init(bar_full_b(s), 1);                 // the weight loader (+ bulk-copy bytes)
+        mbar_init(bar_empty_b(s), 1);                // tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_tfull(b), 1);                  // tcgen05.commit
@@ -389,7 +427,8 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
     float4* s_wgt = reinterpret_cast<float4*>(smem + kOffWgt);
     int* s_pos = reinterpret_cast<int*>(smem + kOffPos);
     int* s_gidx = reinterpret_cast<int*>(smem + kOffGidx);
-    uint32_t it = 0;
+    int sa = 0;
+    uint32_t pha = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const Tile t = tile_of(p, tile);
       producer_bar();  // everyone is done with the previous tile's tap records
@@ -397,20 +436,23 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
       producer_bar();
       Items items;
       load_items(items, ptid, s_pos, s_gidx);
-      for (int c = 0; c < p.n_chunks; ++c, ++it) {
-        const int s = it & 1;
-        mbar_wait(bar_empty(s), ((it >> 1) & 1) ^ 1);
-        const uint32_t a_stage = s_base + kOffA + s * kAStageBytes;
-        if (c < p.n_chunks_extra) {
-          fill_extra(p, t, c, ptid, a_stage, items);
+      for (int c = 0; c < p.n_chunks; ++c) {
+        mbar_wait(bar_empty_a(sa), pha ^ 1);
+        const uint32_t a_stage = s_base + kOffA + sa * kAStageBytes;
+        bool is_extra;
+        const int slice = slice_of(c, p.n_chunks_extra, p.n_chunks - p.n_chunks_extra, &is_extra);
+        if (is_extra) {
+          fill_extra(p, t, slice, ptid, a_stage, items);
           // arrive when this thread's copies have landed; the thread moves on
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full(s))
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                           bar_full_a(sa))
                        : "memory");
         } else {
-          fill_warped(p, t, c - p.n_chunks_extra, ptid, a_stage, s_wgt, items);
+          fill_warped(p, t, slice, ptid, a_stage, s_wgt, items);
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-          mbar_arrive(bar_full(s));
+          mbar_arrive(bar_full_a(sa));
         }
+        if (++sa == kStagesA) { sa = 0; pha ^= 1; }
       }
     }
   } else if (warp < kProducerWarps + kEpilogueWarps) {
@@ -460,30 +502,29 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
     }
   } else if (warp == kProducerWarps + kEpilogueWarps) {
     // ===================== MMA issuer =====================
-    uint32_t it = 0, tl = 0;
-    const uint32_t lbo_a = (p.debug & 1) ? 128u : (uint32_t)kPlanePix * 16u;
-    const uint32_t sbo_a = (p.debug & 1) ? (uint32_t)kPlanePix * 16u : 128u;
-    const uint32_t lbo_b = (p.debug & 1) ? 128u : (uint32_t)kCo * 16u;
-    const uint32_t sbo_b = (p.debug & 1) ? (uint32_t)kCo * 16u : 128u;
+    uint32_t tl = 0, pha = 0, phb = 0;
+    int sa = 0, sb = 0;
+    const uint32_t lbo_a = (uint32_t)kPlanePix * 16u, sbo_a = 128u;
+    const uint32_t lbo_b = (uint32_t)kCo * 16u, sbo_b = 128u;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
       const int buf = tl & 1;
       mbar_wait(bar_tempty(buf), ((tl >> 1) & 1) ^ 1);
       tc_fence_after();
-      for (int c = 0; c < p.n_chunks; ++c, ++it) {
-        const int s = it & 1;
-        mbar_wait(bar_full(s), (it >> 1) & 1);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint64_t a0 = make_desc(s_base + kOffA + s * kAStageBytes, lbo_a, sbo_a);
-          const uint64_t b0 = make_desc(s_base + kOffB + s * kBStageBytes, lbo_b, sbo_b);
-          const uint32_t d0 = tmem_base + (uint32_t)(buf * (kRows * kCo));
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * (kRows * kCo));
+      for (int c = 0; c < p.n_chunks; ++c) {
+        mbar_wait(bar_full_a(sa), pha);
+        const uint64_t a0 = make_desc(s_base + kOffA + sa * kAStageBytes, lbo_a, sbo_a);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
+        for (int ks = 0; ks < 2; ++ks) {
+          mbar_wait(bar_full_b(sb), phb);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint64_t b0 = make_desc(s_base + kOffB + sb * kBStageBytes, lbo_b, sbo_b);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int dy = tap / 3, dx = tap - dy * 3;
               // descriptor start addresses advance in 16-byte units
-              const uint64_t bd = b0 + (uint64_t)((tap * 4 + ks * 2) * kCo);
+              const uint64_t bd = b0 + (uint64_t)(tap * 2 * kCo);
               const uint32_t acc = (ks | tap) != 0 ? 1u : (uint32_t)(c != 0);
 #pragma unroll
               for (int r = 0; r < kRows; ++r) {
@@ -492,25 +533,31 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
                 tc_mma_tf32(d0 + (uint32_t)(r * kCo), ad, bd, kIdesc, acc);
               }
             }
+            tc_commit(bar_empty_b(sb));      // weight stage free when these MMAs retire
+            if (ks == 1) {
+              tc_commit(bar_empty_a(sa));    // activation stage free
+              if (c == p.n_chunks - 1) tc_commit(bar_tfull(buf));  // accumulators complete
+            }
           }
-          tc_commit(bar_empty(s));                       // stage free when these MMAs retire
-          if (c == p.n_chunks - 1) tc_commit(bar_tfull(buf));  // accumulators complete
+          __syncwarp();
+          if (++sb == kStagesB) { sb = 0; phb ^= 1; }
         }
-        __syncwarp();
+        if (++sa == kStagesA) { sa = 0; pha ^= 1; }
       }
     }
   } else {
     // ===================== weight loader =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      int sb = 0;
+      uint32_t phb = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < p.n_chunks; ++c, ++it) {
-          const int s = it & 1;
-          mbar_wait(bar_empty(s), ((it >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full(s), kBStageBytes);
-          bulk_g2s(s_base + kOffB + s * kBStageBytes,
-                   reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kBStageBytes,
-                   kBStageBytes, bar_full(s));
+        for (int j = 0; j < 2 * p.n_chunks; ++j) {
+          mbar_wait(bar_empty_b(sb), phb ^ 1);
+          mbar_arrive_expect_tx(bar_full_b(sb), kBStageBytes);
+          bulk_g2s(s_base + kOffB + sb * kBStageBytes,
+                   reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)j * kBStageBytes,
+                   kBStageBytes, bar_full_b(sb));
+          if (++sb == kStagesB) { sb = 0; phb ^= 1; }
         }
       }
     }
@@ -526,16 +573,21 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
   }
 }
 
-// weight [Co=64, Ci, 3, 3] (element strides) -> [Ci/16][tap][k-chunk 4][co 64][4]
+// weight [Co=64, Ce+Cf, 3, 3] (element strides) ->
+//   [slice in consumption order][K-step 2][tap 9][k-chunk 2][co 64][4 channels]
 __global__ void pack_weights_kernel(const float* __restrict__ w, long long s_co, long long s_ci,
                                     long long s_ky, long long s_kx, float* __restrict__ out,
-                                    int total) {
+                                    int n_extra, int n_feat, int total) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int j = idx & 3, co = (idx >> 2) & 63, kc = (idx >> 8) & 3;
-  const int rest = idx >> 10;
-  const int tap = rest % 9, cc = rest / 9;
-  const int ci = cc * kChunk + kc * 4 + j;
+  const int j = idx & 3, co = (idx >> 2) & 63, kc = (idx >> 8) & 1;
+  int rest = idx >> 9;
+  const int tap = rest % 9;
+  rest /= 9;
+  const int ks = rest & 1, c = rest >> 1;
+  bool is_extra;
+  const int slice = slice_of(c, n_extra, n_feat, &is_extra);
+  const int ci = (is_extra ? 0 : n_extra * kChunk) + slice * kChunk + ks * 8 + kc * 4 + j;
   const int ky = tap / 3, kx = tap - ky * 3;
   out[idx] = w[co * s_co + ci * s_ci + ky * s_ky + kx * s_kx];
 }
@@ -551,13 +603,16 @@ extern "C" int64_t dvc_conv3x3_packed_weight_floats(int64_t Co, int64_t Ci) {
 }
 
 extern "C" int dvc_conv3x3_pack_weights(const float* weight, const int64_t w_st[4], int64_t Co,
-                                        int64_t Ci, float* packed, dvc_stream_t stream) {
+                                        int64_t Ce, int64_t Cf, float* packed,
+                                        dvc_stream_t stream) {
   DVC_REQUIRE(weight && packed && w_st, "conv3x3_pack_weights: null pointer");
   DVC_REQUIRE(Co == wc::kCo, "conv3x3_pack_weights: Co must be 64 (got %lld)", (long long)Co);
-  DVC_REQUIRE(Ci > 0 && Ci % wc::kChunk == 0, "conv3x3_pack_weights: Ci must be a multiple of 16");
-  const int total = (int)(Ci * 9 * Co);
+  DVC_REQUIRE(Cf > 0 && Cf % wc::kChunk == 0 && Ce >= 0 && Ce % wc::kChunk == 0,
+              "conv3x3_pack_weights: Ce and Cf must be multiples of 16");
+  const int total = (int)((Ce + Cf) * 9 * Co);
   wc::pack_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      weight, w_st[0], w_st[1], w_st[2], w_st[3], packed, total);
+      weight, w_st[0], w_st[1], w_st[2], w_st[3], packed, (int)(Ce / wc::kChunk),
+      (int)(Cf / wc::kChunk), total);
   return check_launch("pack_weights_kernel");
 }
 

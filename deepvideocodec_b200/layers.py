@@ -15,6 +15,7 @@ output takes the memory format of ``im``.  channels_last with C % 4 == 0 is
 the fast path.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -240,32 +241,42 @@ def motion_compensation_warps(x_ref, feat1, feat2, feat3, mv):
 # ---------------------------------------------------------------------------
 # warp fused into the 3x3 conv that consumes it (tcgen05)
 # ---------------------------------------------------------------------------
-_packed_weights = {}
+_packed_weights = {}   # id(weight) -> (weakref to the weight object, {ce: (key, packed)})
 
 
-def pack_conv3x3_weight(weight):
-    """Re-lay a ``[64, Ci, 3, 3]`` conv weight into the UMMA operand layout.
+def pack_conv3x3_weight(weight, ce=0):
+    """Re-lay a ``[64, ce + cf, 3, 3]`` conv weight into the UMMA operand layout.
 
-    Cached per (storage, version): re-packed only after the parameter changes.
+    ``ce`` is the number of leading input channels that belong to ``extra``.
+    Cached per weight OBJECT (weakly: a freed tensor whose storage address is
+    reused cannot alias), re-packed when its version counter, storage or
+    strides change.
     """
     nat.require_cuda_f32(weight, "pack_conv3x3_weight(weight)")
     co, ci, kh, kw = weight.shape
     if (kh, kw) != (3, 3):
         raise nat.DvcError(f"pack_conv3x3_weight: 3x3 kernels only, got {kh}x{kw}")
     key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
-    hit = _packed_weights.get(weight.device.index)
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    entry = _packed_weights.get(id(weight))
+    if entry is not None and entry[0]() is not weight:     # id reused by another object
+        entry = None
+    if entry is not None and ce in entry[1] and entry[1][ce][0] == key:
+        return entry[1][ce][1]
     n = nat.lib().dvc_conv3x3_packed_weight_floats(co, ci)
-    if n <= 0:
-        raise nat.DvcError(f"pack_conv3x3_weight: need Co == 64 and Ci % 16 == 0, got {co}, {ci}")
+    if n <= 0 or ce % 16 or not 0 <= ce < ci:
+        raise nat.DvcError(f"pack_conv3x3_weight: need Co == 64 and channel counts that are "
+                           f"multiples of 16, got Co={co}, Ci={ci}, Ce={ce}")
     packed = torch.empty(n, dtype=torch.float32, device=weight.device)
     w = weight.detach()
     with nat.device_of(w):
-        rc = nat.lib().dvc_conv3x3_pack_weights(w.data_ptr(), nat.st4(w), co, ci,
+        rc = nat.lib().dvc_conv3x3_pack_weights(w.data_ptr(), nat.st4(w), co, ce, ci - ce,
                                                 packed.data_ptr(), nat.stream_of(w))
     nat.check(rc, "dvc_conv3x3_pack_weights")
-    _packed_weights[weight.device.index] = (key, packed)
+    if entry is None:
+        wid = id(weight)
+        entry = (weakref.ref(weight, lambda _r, wid=wid: _packed_weights.pop(wid, None)), {})
+        _packed_weights[wid] = entry
+    entry[1][ce] = (key, packed)
     return packed
 
 
@@ -315,7 +326,7 @@ def warp_conv3x3(feat, flow, weight, bias=None, extra=None, *, flow_downscale=0,
                            "torch.no_grad() or use flow_warp + conv2d for training")
     feat = _nhwc_dense(feat)
     if packed is None:
-        packed = pack_conv3x3_weight(weight)
+        packed = pack_conv3x3_weight(weight, ce)
     ctx = torch.empty_like(feat) if want_warp else None
     conv = torch.empty((n, co, h, w), dtype=torch.float32, device=feat.device,
                        memory_format=torch.channels_last)

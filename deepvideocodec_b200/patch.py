@@ -17,7 +17,9 @@ reference name (dmc/models/...)                        replacement
 ``FrameContextModel.forward`` (:390)                   ``context.frame_context_forward``
 ``MotionContextModel.compress/decompress`` (:236/:255) ``context.motion_context_(de)compress``
 ``FrameContextModel.compress/decompress`` (:408/:429)  ``context.frame_context_(de)compress``
-``DMC.motion_compensation`` (:497)                     fused 2-launch version below
+``DMC.motion_compensation`` (:497)                     one-launch warps below; in inference, with
+                                                       ``fuse_warp_conv=True``, each warp is fused into
+                                                       the ``conv{1,2,3}_out`` that consumes it (tcgen05)
 ``train.collect_likelihoods_list`` (train.py:74)       ``rate.collect_likelihoods_list``
 =====================================================  =========================================
 
@@ -60,12 +62,43 @@ def _motion_compensation(self, mv, dpb):
     return context1, context2, context3, warpframe
 
 
+def motion_compensation_fused(self, mv, dpb):
+    """``DMC.motion_compensation`` + ``MultiScaleContextFusion.forward``
+    (video_model.py:497-506, :49-66) with every context warp fused into the 3x3
+    convolution that consumes it: the warped contexts are
+    written once (the residual adds need them) and never re-read by
+    ``conv{1,2,3}_out``; mv2 / mv3 are never materialised.  Same sub-modules,
+    same parameters, same return structure; the three fused convs compute in
+    TF32 like cuDNN's default, the rest of the net is the reference's own
+    modules.  Inference only -- with autograd on, the unfused path runs."""
+    import torch
+    if torch.is_grad_enabled() or mv.size(2) % 4 or mv.size(3) % 4 or \
+            any(getattr(self.context_fusion_net, n).out_channels != 64
+                for n in ("conv1_out", "conv2_out", "conv3_out")):
+        return _motion_compensation(self, mv, dpb)
+    f1, f2, f3 = self.multi_scale_feature_extractor(dpb)
+    net = self.context_fusion_net
+    warpframe = layers.flow_warp(dpb["x_ref"], mv)
+    c3, c3_pre = layers.warp_conv3x3(f3, mv, net.conv3_out.weight, net.conv3_out.bias,
+                                     flow_downscale=2)
+    c3_up = net.res_block3_up(net.conv3_up(c3))
+    c3_out = net.res_block3_out(c3_pre)
+    c2, c2_pre = layers.warp_conv3x3(f2, mv, net.conv2_out.weight, net.conv2_out.bias,
+                                     extra=c3_up, flow_downscale=1)
+    c2_up = net.res_block2_up(net.conv2_up(torch.cat((c3_up, c2), dim=1)))
+    c2_out = net.res_block2_out(c2_pre)
+    c1, c1_pre = layers.warp_conv3x3(f1, mv, net.conv1_out.weight, net.conv1_out.bias,
+                                     extra=c2_up)
+    c1_out = net.res_block1_out(c1_pre)
+    return c1 + c1_out, c2 + c2_out, c3 + c3_out, warpframe
+
+
 def _set(obj, name, value):
     _saved.append((obj, name, getattr(obj, name)))
     setattr(obj, name, value)
 
 
-def patch(models_pkg, train_module=None, fuse_context_models=True):
+def patch(models_pkg, train_module=None, fuse_context_models=True, fuse_warp_conv=False):
     """Rebind the hot-path names of the reference ``models`` package (the
     module object of ``dmc/models``).  Idempotent; ``unpatch()`` restores."""
     if _saved:
@@ -89,7 +122,8 @@ def patch(models_pkg, train_module=None, fuse_context_models=True):
         _set(vm.FrameContextModel, "compress", context.frame_context_compress)
         _set(vm.MotionContextModel, "decompress", context.motion_context_decompress)
         _set(vm.FrameContextModel, "decompress", context.frame_context_decompress)
-    _set(vm.DMC, "motion_compensation", _motion_compensation)
+    _set(vm.DMC, "motion_compensation",
+         motion_compensation_fused if fuse_warp_conv else _motion_compensation)
     if train_module is not None:
         _set(train_module, "collect_likelihoods_list", rate.collect_likelihoods_list)
 

@@ -133,13 +133,15 @@ int dvc_warp_multi_fwd(const dvc_warp_task* tasks /* HOST array */, int n_tasks,
  *            dvc_flow_warp_fwd;  out_conv [N,64,H,W] channels_last dense.
  * Cf, Ce multiples of 16; Co = 64.  The weight [64, Ce+Cf, 3, 3] is re-laid
  * once by dvc_conv3x3_pack_weights into dvc_conv3x3_packed_weight_floats()
- * floats ([Ci/16][tap][ci%16/4][co][ci%4], the UMMA K-major operand layout).
+ * floats (16-channel slices in the kernel's consumption order -- `extra` and
+ * `feat` slices alternate --, each as [K-step][tap][4-channel group][co][4], the
+ * UMMA K-major operand layout; the packing therefore depends on the Ce/Cf split).
  * PyTorch's cuDNN convolutions run in TF32 by default; this kernel truncates
  * the operands to TF32 in the tensor core and accumulates in fp32.
  * ------------------------------------------------------------------------- */
 int64_t dvc_conv3x3_packed_weight_floats(int64_t Co, int64_t Ci);
 int dvc_conv3x3_pack_weights(const float* weight, const int64_t w_st[4],
-                             int64_t Co, int64_t Ci, float* packed,
+                             int64_t Co, int64_t Ce, int64_t Cf, float* packed,
                              dvc_stream_t stream);
 int dvc_warp_conv3x3_fwd(const float* feat, const float* flow,
                          const float* extra /*[opt]*/,

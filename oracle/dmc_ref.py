@@ -75,6 +75,66 @@ def motion_compensation_warps(x_ref, feat1, feat2, feat3, mv):
 # --------------------------------------------------------------------------
 # piece 2: quantisation  (utils.py:149-152, video_model.py:152-216, 222-224)
 # --------------------------------------------------------------------------
+class ResBlockRef(torch.nn.Module):
+    """``ResBlock(channel)`` with the defaults the context-fusion net uses
+    (layers.py:59-81: LeakyReLU(0.01) -> conv -> LeakyReLU -> conv, + x)."""
+
+    def __init__(self, channel, slope=0.01):
+        super().__init__()
+        self.conv1 = torch.nn.Conv2d(channel, channel, 3, padding=1)
+        self.conv2 = torch.nn.Conv2d(channel, channel, 3, padding=1)
+        self.slope = slope
+
+    def forward(self, x):
+        out = F.leaky_relu(x, self.slope)
+        out = self.conv1(out)
+        out = F.leaky_relu(out, self.slope)
+        out = self.conv2(out)
+        return x + out
+
+
+def _subpel_conv3x3(in_ch, out_ch, r):
+    # layers.py:52-56
+    return torch.nn.Sequential(torch.nn.Conv2d(in_ch, out_ch * r ** 2, 3, padding=1),
+                               torch.nn.PixelShuffle(r))
+
+
+class MultiScaleContextFusionRef(torch.nn.Module):
+    """Restatement of ``MultiScaleContextFusion`` (video_model.py:37-66) with the
+    reference's parameter names, so a reference ``state_dict`` loads."""
+
+    def __init__(self, channel_in=64, channel_out=64):
+        super().__init__()
+        c = channel_out
+        self.conv3_up = _subpel_conv3x3(channel_in, c, 2)
+        self.res_block3_up = ResBlockRef(c)
+        self.conv3_out = torch.nn.Conv2d(c, c, 3, padding=1)
+        self.res_block3_out = ResBlockRef(c)
+        self.conv2_up = _subpel_conv3x3(c * 2, c, 2)
+        self.res_block2_up = ResBlockRef(c)
+        self.conv2_out = torch.nn.Conv2d(c * 2, c, 3, padding=1)
+        self.res_block2_out = ResBlockRef(c)
+        self.conv1_out = torch.nn.Conv2d(c * 2, c, 3, padding=1)
+        self.res_block1_out = ResBlockRef(c)
+
+    def forward(self, context1, context2, context3):
+        context3_up = self.res_block3_up(self.conv3_up(context3))
+        context3_out = self.res_block3_out(self.conv3_out(context3))
+        cat32 = torch.cat((context3_up, context2), dim=1)
+        context2_up = self.res_block2_up(self.conv2_up(cat32))
+        context2_out = self.res_block2_out(self.conv2_out(cat32))
+        context1_out = self.res_block1_out(self.conv1_out(torch.cat((context2_up, context1), dim=1)))
+        return context1 + context1_out, context2 + context2_out, context3 + context3_out
+
+
+def motion_compensation(x_ref, feat1, feat2, feat3, mv, fusion_net):
+    """``DMC.motion_compensation`` (video_model.py:497-506) given the three
+    reference features: warps, then the context-fusion net."""
+    c1, c2, c3, wf = motion_compensation_warps(x_ref, feat1, feat2, feat3, mv)
+    c1, c2, c3 = fusion_net(c1, c2, c3)
+    return c1, c2, c3, wf
+
+
 def quantize_ste(x):
     """``quantize_ste`` (utils.py:149-152): round-half-even forward, identity
     backward."""

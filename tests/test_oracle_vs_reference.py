@@ -148,3 +148,24 @@ def test_stock_dmc_forward_regression(ref):
     assert len(net.state_dict()) == 438
     aux = [float(a) for a in net.aux_loss()]
     assert abs(aux[0] - 2641.55) < 0.5 and abs(aux[1] - 2636.41) < 0.5
+
+
+def test_context_fusion_net_restatement(ref):
+    """oracle MultiScaleContextFusionRef == stock MultiScaleContextFusion
+    (video_model.py:37-66) under the stock module's own state_dict; it anchors
+    the fused warp + conv drop-in (tests/test_gpu_warp_conv.py)."""
+    vm = ref["vm"]
+    torch.manual_seed(5)
+    stock = vm.MultiScaleContextFusion().eval()
+    mine = dmc_ref.MultiScaleContextFusionRef().eval()
+    missing, unexpected = mine.load_state_dict(stock.state_dict(), strict=True)
+    assert not missing and not unexpected
+    g = torch.Generator().manual_seed(6)
+    c1 = torch.randn(1, 64, 16, 32, generator=g)
+    c2 = torch.randn(1, 64, 8, 16, generator=g)
+    c3 = torch.randn(1, 64, 4, 8, generator=g)
+    with torch.no_grad():
+        a = stock(c1, c2, c3)
+        b = mine(c1, c2, c3)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

@@ -10,6 +10,8 @@ from deepvideocodec_b200 import layers
 dev = torch.device("cuda:0")
 H, W = int(os.environ.get("H", 1088)), int(os.environ.get("W", 1920))
 CE = int(os.environ.get("CE", 64))
+DEBUG = int(os.environ.get("DEBUG", 0))
+FLOW = os.environ.get("FLOW", "smooth")
 torch.manual_seed(0)
 NSETS = 3
 cl = torch.channels_last
@@ -17,10 +19,22 @@ feats = [torch.randn(1, 64, H, W, device=dev).contiguous(memory_format=cl) for _
 extras = [torch.randn(1, CE, H, W, device=dev).contiguous(memory_format=cl) for _ in range(NSETS)] if CE else [None] * NSETS
 lp = F.avg_pool2d(torch.randn(1, 2, H, W, device=dev), 31, 1, 15)
 flow = lp / lp.std() * 4.0
+if FLOW == "iid":
+    flow = torch.randn(1, 2, H, W, device=dev) * 16.0
+elif FLOW == "rigid":
+    flow = torch.zeros(1, 2, H, W, device=dev) + 2.3
 weight = torch.randn(64, CE + 64, 3, 3, device=dev) * 0.05
 w_cl = weight.contiguous(memory_format=cl)
 bias = torch.randn(64, device=dev)
-packed = layers.pack_conv3x3_weight(weight)
+if os.environ.get("OLD_ABI"):      # A/B against a build that predates the Ce/Cf-aware packing
+    import ctypes
+    from deepvideocodec_b200 import _native as nat
+    fn = nat.lib().dvc_conv3x3_pack_weights
+    fn.argtypes = [ctypes.c_void_p, nat._P4, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    packed = torch.empty((CE + 64) * 9 * 64, device=dev)
+    assert fn(weight.data_ptr(), nat.st4(weight), 64, CE + 64, packed.data_ptr(), nat.stream_of(weight)) == 0
+else:
+    packed = layers.pack_conv3x3_weight(weight, CE)
 
 
 def timeit(fn, n=30, warm=5):
@@ -37,7 +51,7 @@ def timeit(fn, n=30, warm=5):
 
 
 def fused(i):
-    return layers.warp_conv3x3(feats[i % NSETS], flow, weight, bias, extras[i % NSETS], packed=packed)
+    return layers.warp_conv3x3(feats[i % NSETS], flow, weight, bias, extras[i % NSETS], packed=packed, _debug=DEBUG)
 
 
 def unfused_nhwc(i):
@@ -62,14 +76,15 @@ def conv_only_nhwc(i, xs=[None]):
     return F.conv2d(xs[0], w_cl, bias, padding=1)
 
 
-res = {"H": H, "W": W, "Ce": CE, "Cf": 64}
+res = {"H": H, "W": W, "Ce": CE, "Cf": 64, "debug": DEBUG, "flow": FLOW}
 with torch.no_grad():
     torch.backends.cudnn.benchmark = True
     torch.backends.cudnn.allow_tf32 = True
     res["fused_us"] = timeit(fused)
-    res["warp_plus_cudnn_nhwc_tf32_us"] = timeit(unfused_nhwc)
-    res["cudnn_conv_only_nhwc_tf32_us"] = timeit(conv_only_nhwc)
-    res["warp_plus_cudnn_nchw_tf32_us"] = timeit(unfused_nchw, n=10, warm=3)
+    if not os.environ.get("FUSED_ONLY"):
+        res["warp_plus_cudnn_nhwc_tf32_us"] = timeit(unfused_nhwc)
+        res["cudnn_conv_only_nhwc_tf32_us"] = timeit(conv_only_nhwc)
+        res["warp_plus_cudnn_nchw_tf32_us"] = timeit(unfused_nchw, n=10, warm=3)
     flops = 2.0 * H * W * 64 * (CE + 64) * 9
     res["fused_tflops"] = flops / res["fused_us"] / 1e6
     # algorithmic HBM bytes: read feat, extra, flow; write ctx, conv
@@ -81,4 +96,4 @@ with torch.no_grad():
     res["conv_vs_cudnn_tf32_max_abs"] = float((v1 - v2).abs().max())
     res["conv_scale"] = float(v2.abs().max())
 print(json.dumps(res, indent=1))
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"warp_conv_bench_{H}x{W}_ce{CE}.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"warp_conv_bench_{H}x{W}_ce{CE}_{FLOW}_d{DEBUG}.json"), "w"), indent=1)
