@@ -284,6 +284,215 @@ warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
     warp_tile_strided(t, tile);
 }
 
+
+// ---------------------------------------------------------------------------
+// planar (NCHW) path -- the reference's own memory format -- with the source
+// tile staged in shared memory.
+//
+// The strided path above issues 4 scalar gathers per output element and is
+// bound by L1 wavefronts (~0.36 of the HBM copy peak for C = 64).  A pixel's tap
+// geometry is the same for every channel, so a CTA (32 x 8 pixels) computes its
+// 256 tap records once, takes the bounding box of the taps, and then for every
+// channel plane copies that box into shared memory with 16-byte cp.async
+// (L2 -> smem, no registers, 4 planes in flight) and gathers from there.  If the
+// box does not fit (incoherent flow) the CTA falls back to the global gathers.
+// Same arithmetic as every other path (make_taps / blend): bit-identical.
+// ---------------------------------------------------------------------------
+constexpr int kPlPx = 2;                              // pixels per thread (columns w, w + 32)
+constexpr int kPlTileW = 32 * kPlPx, kPlTileH = 8;    // 64 x 8 pixels per CTA
+constexpr int kPlBoxW4 = 28, kPlBoxH = 26;            // staged box: <= 112 x 26 floats
+constexpr int kPlBufFloats = kPlBoxW4 * 4 * kPlBoxH;  // 2912 floats = 11648 B
+#ifndef DVC_PLANAR_BUFS
+#define DVC_PLANAR_BUFS 4
+#endif
+constexpr int kPlBufs = DVC_PLANAR_BUFS;              // channel planes in flight
+constexpr int kPlSlots = (kPlBoxW4 * kPlBoxH + kThreads - 1) / kThreads;  // float4 per thread, 3
+constexpr int kPlSmemBytes = kPlBufs * kPlBufFloats * 4;
+
+// kStaged = true : tiles whose tap box fits are gathered from shared memory, others return;
+// kStaged = false: the complementary launch (no shared memory -> all of L1 for the
+//                  incoherent gathers) takes the tiles the first one left, others return.
+// Both evaluate the same deterministic box test, so no flag buffer is needed.
+template <bool kStaged>
+__global__ void __launch_bounds__(kThreads, 4)
+warp_planar_kernel(const __grid_constant__ WarpTask t) {
+  extern __shared__ __align__(16) float pl_smem[];
+  __shared__ int s_red[32];   // static: the gather launch has no dynamic shared memory
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile = blockIdx.x;
+  const int tx = tile % t.tiles_x;
+  const int rest = tile / t.tiles_x;
+  const int ty = rest % t.tiles_y;
+  const int n = rest / t.tiles_y;
+  const int H = t.g.H, W = t.g.W;
+  const int h = ty * kPlTileH + wid;
+  const int hc = min(h, H - 1);
+  const float* __restrict__ fl = t.flow + n * t.fl_n;
+
+  Taps T[kPlPx];
+  bool valid[kPlPx];
+  int wcl[kPlPx];
+  int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+#pragma unroll
+  for (int k = 0; k < kPlPx; ++k) {
+    const int w = tx * kPlTileW + k * 32 + lane;
+    valid[k] = (w < W) && (h < H);
+    wcl[k] = min(w, W - 1);          // out-of-tile lanes replay a real pixel: the box is unaffected
+    const float fx = fetch_flow(fl, t.fl_h, t.fl_w, hc, wcl[k], t.flow_level);
+    const float fy = fetch_flow(fl + t.fl_c, t.fl_h, t.fl_w, hc, wcl[k], t.flow_level);
+    T[k] = make_taps(t.g, hc, wcl[k], fx, fy);
+    xmin = min(xmin, T[k].x0); xmax = max(xmax, T[k].x0);
+    ymin = min(ymin, T[k].y0); ymax = max(ymax, T[k].y0);
+  }
+
+  // ---- bounding box of the tile's taps -----------------------------------------
+  xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+  ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+  if (lane == 0) {
+    s_red[wid] = xmin;
+    s_red[8 + wid] = xmax;
+    s_red[16 + wid] = ymin;
+    s_red[24 + wid] = ymax;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    xmin = min(xmin, s_red[i]);
+    xmax = max(xmax, s_red[8 + i]);
+    ymin = min(ymin, s_red[16 + i]);
+    ymax = max(ymax, s_red[24 + i]);
+  }
+  const int bx0 = xmin & ~3;                       // 16-byte aligned column
+  const int bx1 = min(xmax + 1, W - 1), by0 = ymin, by1 = min(ymax + 1, H - 1);
+  const int hh = by1 - by0 + 1;
+  int w4 = (bx1 - bx0 + 4) >> 2;                   // box width in float4 columns
+  // an odd float4 pitch spreads the rows of a box over the banks (pitch = 4 mod 8 words)
+  const int pitch4 = (w4 & 1) ? w4 : w4 + 1;
+  const int pitch = pitch4 * 4;
+
+  const float* __restrict__ im_n = t.im + n * t.im_n;
+  float* __restrict__ po = t.out + n * t.out_n + hc * t.out_h;
+
+  const bool fits = pitch4 <= kPlBoxW4 && hh <= kPlBoxH;
+  if (fits != kStaged) return;
+  if (!kStaged) {
+    // ---- incoherent flow: global gathers (warp_tile_strided's arithmetic), both
+    // pixels of the thread interleaved so 8 independent loads are in flight per channel
+    const float* p_nw[kPlPx];
+    int o_e[kPlPx];
+    long long o_s[kPlPx];
+    float* pk[kPlPx];
+#pragma unroll
+    for (int k = 0; k < kPlPx; ++k) {
+      p_nw[k] = im_n + T[k].y0 * t.im_h + T[k].x0;
+      o_e[k] = T[k].dx ? 1 : 0;
+      o_s[k] = T[k].dy ? t.im_h : 0;
+      pk[k] = po + wcl[k] * t.out_w;
+    }
+#pragma unroll 2
+    for (int c = 0; c < t.C; ++c) {
+#pragma unroll
+      for (int k = 0; k < kPlPx; ++k) {
+        const bool in_e = T[k].dx != 0, in_s = T[k].dy != 0;
+        const float vnw = __ldg(p_nw[k]);
+        float vne = __ldg(p_nw[k] + o_e[k]);
+        float vsw = __ldg(p_nw[k] + o_s[k]);
+        float vse = __ldg(p_nw[k] + o_s[k] + o_e[k]);
+        vne = in_e ? vne : 0.f;
+        vsw = in_s ? vsw : 0.f;
+        vse = (in_e && in_s) ? vse : 0.f;
+        if (valid[k]) *pk[k] = blend(vnw, vne, vsw, vse, T[k]);
+        p_nw[k] += t.im_c;
+        pk[k] += t.out_c;
+      }
+    }
+    return;
+  }
+
+  // ---- staged path ------------------------------------------------------------------
+  // this thread's share of a box copy: the same (row, float4 column) slots for every
+  // plane; the source pointers advance by one plane per use
+  const float* src[kPlSlots];
+  uint32_t dst_off[kPlSlots];
+  const int n_vec = w4 * hh;
+#pragma unroll
+  for (int k = 0; k < kPlSlots; ++k) {
+    const int e = threadIdx.x + k * kThreads;
+    const int r = e / w4, c4 = e - r * w4;
+    src[k] = im_n + (long long)(by0 + r) * t.im_h + bx0 + c4 * 4;
+    dst_off[k] = e < n_vec ? (uint32_t)(r * pitch + c4 * 4) * 4u : 0xffffffffu;
+  }
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(pl_smem);
+  int issued = 0;   // planes issued so far (also selects the buffer)
+  auto issue = [&]() {
+    if (issued < t.C) {
+      const uint32_t buf = s_base + (uint32_t)((issued % kPlBufs) * kPlBufFloats) * 4u;
+#pragma unroll
+      for (int k = 0; k < kPlSlots; ++k) {
+        if (dst_off[k] != 0xffffffffu)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf + dst_off[k]),
+                       "l"(src[k])
+                       : "memory");
+        src[k] += t.im_c;
+      }
+    }
+    ++issued;
+    asm volatile("cp.async.commit_group;" ::: "memory");   // empty groups keep the count uniform
+  };
+#pragma unroll
+  for (int c = 0; c < kPlBufs - 1; ++c) issue();
+
+  int i_nw[kPlPx], i_ne[kPlPx], i_sw[kPlPx], i_se[kPlPx];
+  float* pk[kPlPx];
+#pragma unroll
+  for (int k = 0; k < kPlPx; ++k) {
+    const bool in_e = T[k].dx != 0, in_s = T[k].dy != 0;
+    i_nw[k] = (T[k].y0 - by0) * pitch + (T[k].x0 - bx0);
+    i_ne[k] = i_nw[k] + (in_e ? 1 : 0);
+    i_sw[k] = i_nw[k] + (in_s ? pitch : 0);
+    i_se[k] = i_sw[k] + (in_e ? 1 : 0);
+    pk[k] = po + wcl[k] * t.out_w;
+  }
+#pragma unroll 1
+  for (int c = 0; c < t.C; ++c) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPlBufs - 2) : "memory");   // plane c has landed
+    __syncthreads();            // ... for every thread; and everyone is done with plane c - 1
+    issue();                    // into the buffer plane c - 1 used
+    const float* __restrict__ b = pl_smem + (c % kPlBufs) * kPlBufFloats;
+#pragma unroll
+    for (int k = 0; k < kPlPx; ++k) {
+      const bool in_e = T[k].dx != 0, in_s = T[k].dy != 0;
+      const float vnw = b[i_nw[k]];
+      float vne = b[i_ne[k]], vsw = b[i_sw[k]], vse = b[i_se[k]];
+      vne = in_e ? vne : 0.f;
+      vsw = in_s ? vsw : 0.f;
+      vse = (in_e && in_s) ? vse : 0.f;
+      if (valid[k]) __stcs(pk[k], blend(vnw, vne, vsw, vse, T[k]));
+      pk[k] += t.out_c;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+static bool planar_ok(const WarpTask& t, const dvc_warp_task& in) {
+  // unit pixel stride, 16-byte aligned rows / planes / samples, rows of whole float4
+  return t.mode == kModeStrided && in.C >= 8 && t.im_w == 1 && (in.W % 4) == 0 &&
+         (t.im_h % 4) == 0 && (t.im_c % 4) == 0 && (t.im_n % 4) == 0 && t.im_h >= in.W &&
+         aligned16(in.im);
+}
+
+static int launch_planar(WarpTask t, const dvc_warp_task& in, cudaStream_t stream) {
+  t.tiles_x = (int)((in.W + kPlTileW - 1) / kPlTileW);
+  t.tiles_y = (int)((in.H + kPlTileH - 1) / kPlTileH);
+  const long long nb = (long long)t.tiles_x * t.tiles_y * in.N;
+  DVC_REQUIRE(nb < 2147483647LL, "flow_warp: too many tiles");
+  warp_planar_kernel<true><<<(unsigned)nb, kThreads, kPlSmemBytes, stream>>>(t);
+  int rc = check_launch("warp_planar_kernel<staged>");
+  if (rc) return rc;
+  warp_planar_kernel<false><<<(unsigned)nb, kThreads, 0, stream>>>(t);
+  return check_launch("warp_planar_kernel<gather>");
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -346,14 +555,28 @@ static int launch_batch(const dvc_warp_task* tasks, int n_tasks, int flags,
   DVC_REQUIRE(tasks && n_tasks >= 1 && n_tasks <= kMaxTasks,
               "warp_multi: n_tasks must be in [1,%d]", kMaxTasks);
   WarpBatch batch;
-  batch.n_tasks = n_tasks;
   long long total = 0;
-  for (int i = 0; i < n_tasks; ++i) {
-    int rc = build_task(batch.t[i], tasks[i], flags);
-    if (rc) return rc;
-    batch.t[i].first_block = (int)total;
-    total += batch.t[i].n_blocks;
+  int kept = 0;
+  static int planar = -1;   // tuning knob (not API): DVC_WARP_PLANAR=0 keeps NCHW on the strided path
+  if (planar < 0) {
+    const char* e = getenv("DVC_WARP_PLANAR");
+    planar = e ? atoi(e) : 1;
   }
+  for (int i = 0; i < n_tasks; ++i) {
+    int rc = build_task(batch.t[kept], tasks[i], flags);
+    if (rc) return rc;
+    if (planar && planar_ok(batch.t[kept], tasks[i])) {   // NCHW features: own launch
+      rc = launch_planar(batch.t[kept], tasks[i], stream);
+      if (rc) return rc;
+      continue;
+    }
+    batch.t[kept].first_block = (int)total;
+    total += batch.t[kept].n_blocks;
+    ++kept;
+  }
+  n_tasks = kept;
+  batch.n_tasks = n_tasks;
+  if (n_tasks == 0) return DVC_OK;
   for (int i = n_tasks; i < kMaxTasks; ++i) batch.t[i] = batch.t[0];
   DVC_REQUIRE(total < 2147483647LL, "warp_multi: grid too large");
   // proportional interleave: quota[k] ~ n_blocks[k] * 32 / total (>= 1)
