@@ -474,9 +474,17 @@ warp_planar_kernel(const __grid_constant__ WarpTask t) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+static int planar_min_c() {   // tuning knob (not API)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVC_WARP_PLANAR_MINC");
+    v = e ? atoi(e) : 8;
+  }
+  return v;
+}
 static bool planar_ok(const WarpTask& t, const dvc_warp_task& in) {
   // unit pixel stride, 16-byte aligned rows / planes / samples, rows of whole float4
-  return t.mode == kModeStrided && in.C >= 8 && t.im_w == 1 && (in.W % 4) == 0 &&
+  return t.mode == kModeStrided && in.C >= planar_min_c() && t.im_w == 1 && (in.W % 4) == 0 &&
          (t.im_h % 4) == 0 && (t.im_c % 4) == 0 && (t.im_n % 4) == 0 && t.im_h >= in.W &&
          aligned16(in.im);
 }
