@@ -23,12 +23,46 @@ import torch
 
 from . import _native as nat
 
-__all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "build_indexes", "collect",
+__all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "auto_stream_symbols", "build_indexes", "collect",
            "decode_stage_a", "decode_stage_b", "pmf_to_quantized_cdf", "quantize_symbols",
            "rans_decode", "rans_encode", "rans_encode_async", "stream_symbols_of"]
 
 MAGIC = 0x31435644                     # "DVC1"
 DEFAULT_STREAM_SYMBOLS = int(os.environ.get("DVC_RANS_STREAM_SYMBOLS", "4096"))
+MIN_STREAMS = int(os.environ.get("DVC_RANS_MIN_STREAMS", "0"))   # 0: policy below is off
+MIN_STREAM_SYMBOLS = 256
+
+
+def auto_stream_symbols(n_symbols):
+    """Sub-stream length used when the caller does not choose one.
+
+    Range coding is serial inside a sub-stream (~0.1 us per symbol), so a launch
+    lasts ``stream_symbols`` x that no matter how few symbols there are.  With
+    ``DVC_RANS_MIN_STREAMS = k > 0`` a short tensor (the hyper-latent z: 32 640
+    symbols at 1080p) is cut into at least k pieces of a power-of-two length:
+    k = 64 makes a 1080p frame's encode 2.5x and decode 1.8x shorter, but costs
+    ~12 bytes per piece -- +0.3 % bytes at 7 bits/symbol, +4 % at 0.5 bits/symbol
+    (profiles/r01_coder_bench.json, "auto").  Bytes matter more than a
+    millisecond to a codec, so the default is off; the z coder is overlapped with
+    the convolutions that follow it instead (``overlap=True``).  The length is
+    recorded in the container header, so decoders need no matching policy."""
+    s = DEFAULT_STREAM_SYMBOLS
+    if s <= 0 or MIN_STREAMS <= 0:
+        return s
+    while s > MIN_STREAM_SYMBOLS and n_symbols < MIN_STREAMS * s:
+        s //= 2
+    return s
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _side_streams[device.index] = s
+    return s
 
 
 def _dev_i32(t, name):
@@ -151,23 +185,28 @@ def _status_word(device):
 class PendingStreams:
     """Bit streams of one ``rans_encode_async`` call, still on the device."""
 
-    def __init__(self, out, out_bytes, status, cap, keep):
+    def __init__(self, out, out_bytes, status, cap, keep, done=None):
         self.out, self.out_bytes, self.status, self.cap, self._keep = out, out_bytes, status, cap, keep
+        self.done = done       # CUDA event when the encoder ran on the side stream
 
     def result(self):
         return collect([self])[0]
 
 
 def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, scales=None,
-                      scale_table=None, scale_bound=0.11, stream_symbols=None):
+                      scale_table=None, scale_bound=0.11, stream_symbols=None, overlap=False):
     """Launch the encoder for one tensor ``[N,C,H,W]``; no host synchronisation.
 
     Symbols: ``symbols`` (int32) or ``round(x - means)``.  Table indexes:
     ``indexes`` (int), or derived from ``scales`` like ``build_indexes``, or --
     neither -- the channel number.  ``collect`` turns pending results into
-    ``bytes`` with a single device->host round trip for any number of them."""
-    if stream_symbols is None:
-        stream_symbols = DEFAULT_STREAM_SYMBOLS
+    ``bytes`` with a single device->host round trip for any number of them.
+
+    ``overlap=True`` runs the encoder on a per-device side stream (ordered after
+    everything already queued on the current stream): the coder keeps a handful
+    of warps busy for a fraction of a millisecond, and whatever the caller
+    launches next (the hyper-decoder convolutions) proceeds beside it instead of
+    behind it.  ``collect`` joins the streams."""
     src = x if x is not None else symbols
     if src is None or (x is not None and symbols is not None):
         raise ValueError("give exactly one of x / symbols")
@@ -185,6 +224,8 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
         symbols = symbols.to(torch.int32).contiguous()
     ip, sp, tp, T, sst, keep = _index_args(indexes, scales, scale_table, src.shape, dev)
     L = c * h * w
+    if stream_symbols is None:
+        stream_symbols = auto_stream_symbols(L)
     lib = nat.lib()
     cap = lib.dvc_rans_max_bytes(L, int(stream_symbols))
     scratch_bytes = lib.dvc_rans_scratch_bytes(n, L, int(stream_symbols))
@@ -194,15 +235,25 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
     out_bytes = torch.empty(n, dtype=torch.int64, device=dev)
     scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
     status = _status_word(dev)
+    done = None
     with nat.device_of(src):
+        stream = nat.stream_of(src)
+        if overlap:
+            side = _side_stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            stream = side.cuda_stream
         rc = lib.dvc_rans_encode(
             nat.ptr(x), nat.ptr(means), nat.ptr(symbols), ip, sp, tp, T, float(scale_bound),
             tables.cdf.data_ptr(), tables.size.data_ptr(), tables.offset.data_ptr(),
             tables.cdf.size(0), tables.cdf.size(1), out.data_ptr(), cap, out_bytes.data_ptr(),
             scratch.data_ptr(), status.data_ptr(), n, c, h, w, nat.opt_st4(x),
-            nat.opt_st4(means), sst, int(stream_symbols), nat.stream_of(src))
+            nat.opt_st4(means), sst, int(stream_symbols), stream)
+        if overlap:
+            done = torch.cuda.Event()
+            done.record(side)
     nat.check(rc, "dvc_rans_encode")
-    return PendingStreams(out, out_bytes, status, cap, keep + [x, means, symbols, scratch])
+    # every tensor the side stream touches stays referenced until collect() has joined it
+    return PendingStreams(out, out_bytes, status, cap, keep + [x, means, symbols, scratch], done)
 
 
 def collect(pendings):
@@ -210,6 +261,9 @@ def collect(pendings):
     one D2H copy of all payload bytes."""
     if not pendings:
         return []
+    for p in pendings:
+        if p.done is not None:
+            torch.cuda.current_stream(p.out.device).wait_event(p.done)
     status = pendings[0].status
     sizes = torch.cat([p.out_bytes for p in pendings] + [status.to(torch.int64)]).cpu().tolist()
     if sizes[-1] != 0:

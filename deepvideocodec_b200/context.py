@@ -282,7 +282,9 @@ def _compress_head(self, y):
     from . import coder
     eb = self.entropy_bottleneck
     z = self.hyper_encoder(y)
-    z_pending = coder.rans_encode_async(_coder_tables(eb), x=z, means=_medians(eb).expand_as(z))
+    # side stream: the hyper-decoder / prior convolutions run beside the z coder
+    z_pending = coder.rans_encode_async(_coder_tables(eb), x=z, means=_medians(eb).expand_as(z),
+                                        overlap=True)
     # z_hat = decompress(compress(z)) = round(z - median) + median: the likelihood
     # kernel's z_hat output (bit-identical, tests/test_gpu_coder.py)
     _, z_hat, _ = eb_forward(eb, z, training=False, want_outputs=False, want_zhat=True)

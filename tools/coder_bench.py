@@ -115,14 +115,22 @@ def main():
             res["cpu_c_oracle"] = {"encode_ms": 1e3 * t_enc, "decode_ms": 1e3 * t_dec,
                                    "bytes": sum(len(s) for s in stock), "threads": 1}
             res["bits_per_symbol"] = 8 * sum(len(s) for s in stock) / n_sym
-            for S in (256, 1024, 4096, 16384, 65536):
-                def enc():
-                    # both checkerboard passes of a model = one launch (as the product does)
+            for S in (256, 1024, 4096, 16384, 65536, "auto"):
+                def enc(S=S):
+                    # both checkerboard passes of a model = one launch (as the product does);
+                    # "auto" = the product's defaults: per-tensor sub-stream length
+                    # (coder.auto_stream_symbols) and the z coder on the side stream
+                    auto = S == "auto"
+                    ps = [coder.rans_encode_async(eb._tables(), x=z, means=med.expand_as(z),
+                                                  stream_symbols=None if auto else S, overlap=auto)
+                          for z in zs]
                     ps = [coder.rans_encode_async(gc._tables(), x=q, scales=s,
-                                                  scale_table=gc.scale_table, stream_symbols=S)
-                          for q, s in pairs]
-                    ps += [coder.rans_encode_async(eb._tables(), x=z, means=med.expand_as(z),
-                                                   stream_symbols=S) for z in zs]
+                                                  scale_table=gc.scale_table,
+                                                  stream_symbols=None if auto else S)
+                          for q, s in pairs] + ps
+                    for p in ps:
+                        if p.done is not None:
+                            torch.cuda.current_stream().wait_event(p.done)
                     return ps
                 t_e = ev_time(enc)
                 t0 = time.perf_counter()
