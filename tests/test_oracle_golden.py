@@ -117,3 +117,52 @@ def test_rate_golden(golden_dir):
     assert sorted(info) == sorted(keys)
     for k in keys:
         assert torch.equal(torch.as_tensor(info[k]), _t(z, "info." + k)), k
+
+
+def test_model_capture_pins_the_oracle(golden_dir):
+    """Model-driven regime: every hot-path tensor recorded while the
+    stock reference DMC (random init) coded three 64x64 frames on the CPU
+    (tests/golden/make_golden_model.py).  The oracle restatement must reproduce
+    each of them bit for bit from the recorded inputs."""
+    z = np.load(os.path.join(golden_dir, "model_capture.npz"))
+    oem = _oem()
+    gc = oem.GaussianConditional(None).eval()
+    n_checked = 0
+    for f in range(2):
+        for k in range(4):                                   # x_ref, feature 1..3
+            out = dmc_ref.flow_warp(_t(z, f"f{f}.warp{k}.im"), _t(z, f"f{f}.warp{k}.flow"))
+            assert torch.equal(out, _t(z, f"f{f}.warp{k}.out")), (f, k)
+        for k in range(2):
+            assert torch.equal(dmc_ref.bilinear_down2(_t(z, f"f{f}.down{k}.in")),
+                               _t(z, f"f{f}.down{k}.out")), (f, k)
+        # the recorded pyramid is what the recorded warps used (video_model.py:499-504)
+        mv2, mv3 = dmc_ref.flow_pyramid(_t(z, f"f{f}.down0.in"))
+        assert torch.equal(mv2, _t(z, f"f{f}.warp2.flow")) and torch.equal(mv3, _t(z, f"f{f}.warp3.flow"))
+        for label in ("motion", "frame"):
+            p = f"f{f}.{label}."
+            y, mu, sg, prior = (_t(z, p + s) for s in ("y", "means", "scales", "prior"))
+            y_hat, mh, sh = dmc_ref.dual_prior(y, mu, sg, lambda _params: prior)
+            assert torch.equal(y_hat, _t(z, p + "y_hat"))
+            assert torch.equal(mh, _t(z, p + "means_hat")) and torch.equal(sh, _t(z, p + "scales_hat"))
+            with torch.no_grad():
+                _, lik = gc(y, sh, means=mh)
+            assert torch.equal(lik, _t(z, p + "y_lik"))
+            eb = oem.EntropyBottleneck(y.size(1) if label == "motion" else 64).eval()
+            eb.load_state_dict({k[len(f"eb.{label}."):]: _t(z, k) for k in z.files
+                                if k.startswith(f"eb.{label}.")})
+            with torch.no_grad():
+                z_out, z_lik = eb(_t(z, p + "z"))
+                z_hat = dmc_ref.quantize_hyper(_t(z, p + "z"), eb._get_medians())
+            assert torch.equal(z_out, _t(z, p + "z_out")) and torch.equal(z_lik, _t(z, p + "z_lik"))
+            assert torch.equal(z_hat, _t(z, p + "z_hat"))
+            n_checked += 1
+    assert n_checked == 4
+    liks = [{label: {"y": _t(z, f"f{f}.{label}.y_lik"), "z": _t(z, f"f{f}.{label}.z_lik")}
+             for label in ("motion", "frame")} for f in range(2)]
+    bpp, info = dmc_ref.collect_likelihoods_list(liks, int(z["num_pixels"]))
+    assert torch.equal(bpp, _t(z, "bpp_loss"))
+    for k, v in info.items():
+        assert float(v) == float(z["info." + k]), k
+    # the regime this fixture exists for: most likelihoods sit on the 1e-9 floor
+    floor = np.mean([np.mean(z[f"f{f}.{m}.y_lik"] <= 1e-9) for f in range(2) for m in ("motion", "frame")])
+    assert floor > 0.5
