@@ -77,9 +77,6 @@ constexpr int kBStageBytes = 9 * 2 * kCo * 16;    // 18432: the weights of ONE K
 // stores already stream, and cache hints on the gathers themselves changed nothing)
 #define WC_EPI_ST "st.global.L1::no_allocate.v8.f32"
 #endif
-#ifndef WC_INTERLEAVE
-#define WC_INTERLEAVE 0
-#endif
 constexpr int kStagesA = WC_STAGES_A, kStagesB = WC_STAGES_B;
 constexpr int kProducerWarps = 17, kEpilogueWarps = 4;
 constexpr int kProducerThreads = kProducerWarps * 32;
@@ -123,21 +120,13 @@ struct Params {
   int debug;
 };
 
-// Order in which the 16-channel slices are consumed: all `extra` slices, then
-// all warped ones (WC_INTERLEAVE = 1 alternates them; measured slower, see
-// above).  Returns the slice index within its tensor.
+// Order in which the 16-channel slices are consumed: all `extra` slices, then all
+// warped ones (alternating them was measured slower, see above).  Returns the
+// slice index within its tensor.
 __host__ __device__ inline int slice_of(int c, int n_extra, int n_feat, bool* is_extra) {
-  const int m = WC_INTERLEAVE ? (n_extra < n_feat ? n_extra : n_feat) : 0;
-  if (!WC_INTERLEAVE) {
-    *is_extra = c < n_extra;
-    return c < n_extra ? c : c - n_extra;
-  }
-  if (c < 2 * m) {
-    *is_extra = (c & 1) == 0;
-    return c >> 1;
-  }
-  *is_extra = n_extra > n_feat;
-  return m + (c - 2 * m);
+  (void)n_feat;
+  *is_extra = c < n_extra;
+  return c < n_extra ? c : c - n_extra;
 }
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -290,8 +279,7 @@ __device__ __forceinline__ void compute_taps(const Params& p, const Tile& t, int
 // A producer thread owns the pair (halo column, k-chunk) = (ptid >> 2, ptid & 3)
 // and the 6 halo pixels of that column; 130 x 4 = 520 of the 544 threads work.
 constexpr int kFillThreads = kHaloW * 4;
-constexpr int kBatch = 3;   // vertically adjacent pixels gathered together (12 LDG.128 in flight)
-static_assert(kFillThreads <= kProducerThreads && kHaloH % kBatch == 0, "producer mapping");
+static_assert(kFillThreads <= kProducerThreads, "producer mapping");
 
 // The tap records of a thread's 6 pixels are read from shared memory once per
 // tile and kept in registers: the load phase of a slice is address arithmetic
@@ -334,48 +322,93 @@ __device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int c
   }
 }
 
-__device__ __forceinline__ void fill_warped(const Params& p, const Tile& t, int chunk, int ptid,
-                                            uint32_t a_stage, const float4* s_wgt,
-                                            const Items& it) {
-  if (ptid >= kFillThreads) return;
+// Rows of gathers in flight ahead of the row being blended.  2 would hide more
+// latency but needs 48 registers of tap data: with 736 threads the cap is 80
+// registers and the spills cost more than the latency (measured 777 us at
+// distance 1, 885 us at distance 2; batches without pipelining 801 us).
+#ifndef WC_DIST
+#define WC_DIST 1
+#endif
+constexpr int kDist = WC_DIST;   // rows of gathers in flight ahead of the row being blended
+static_assert(kHaloH % (kDist + 1) == 0, "row buffers must line up across slices");
+
+// One halo pixel's four taps of a 4-channel group, in flight or landed.
+struct RowBuf {
+  float4 a[4];
+};
+
+// Issue the gathers of one (pixel, k-chunk) item; no wait.
+__device__ __forceinline__ void issue_row(const float4* __restrict__ im, int Cf4, int south,
+                                          int pos_i, int gi, RowBuf& b) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  b.a[0] = b.a[1] = b.a[2] = b.a[3] = z;
+  if (gi >= 0) {
+    const unsigned pos = (unsigned)pos_i;
+    const float4* __restrict__ north = im + (pos & kOffMask);
+    const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
+    // ATen skips out-of-bounds taps (their weight is 0 anyway)
+    b.a[0] = ldg4(north);
+    if (e) b.a[1] = ldg4(north + Cf4);
+    if (sth) b.a[2] = ldg4(north + south);
+    if (e && sth) b.a[3] = ldg4(north + south + Cf4);
+  }
+}
+
+// The warped half of K for one tile.  A thread walks its column's 6 halo rows
+// slice after slice as ONE software pipeline: the gathers of row r + 2 are issued
+// before row r is blended and stored, across slice boundaries too (loads only
+// need registers; the stage has to be free for the STS alone), so two rows of
+// gathers are always in flight and the L2 / DRAM latency hides behind the
+// blending and behind the wait for the stage instead of being paid per batch.
+// (Sharing the east taps of neighbouring columns by warp shuffle was also tried:
+// it removes 44 % of the loads of a rigid flow and was SLOWER, 807-921 vs 762-787
+// us -- the gathers are latency-, not bandwidth-limited; an i.i.d. flow with no
+// reuse at all costs only 9 % more than a rigid one.)
+__device__ __forceinline__ void fill_warped_tile(const Params& p, const Tile& t, int ptid,
+                                                 uint32_t s_base, uint32_t bar_full0,
+                                                 uint32_t bar_empty0, int& sa, uint32_t& pha,
+                                                 const float4* s_wgt, const Items& it) {
+  const int n_w = p.n_chunks - p.n_chunks_extra;
+  if (n_w <= 0) return;
   const int Cf4 = p.Cf >> 2;
   const long long sample = (long long)t.n * p.H * p.W * Cf4;
-  const float4* __restrict__ im =
-      reinterpret_cast<const float4*>(p.feat) + sample + chunk * 4 + (ptid & 3);
+  const float4* __restrict__ im = reinterpret_cast<const float4*>(p.feat) + sample + (ptid & 3);
   float4* __restrict__ ow =
-      p.out_warp ? reinterpret_cast<float4*>(p.out_warp) + sample + chunk * 4 + (ptid & 3)
-                 : nullptr;
+      p.out_warp ? reinterpret_cast<float4*>(p.out_warp) + sample + (ptid & 3) : nullptr;
   const int south = p.W * Cf4;
+  const int col = ptid < kFillThreads ? (ptid >> 2) : 0;
+  const bool active = ptid < kFillThreads;
+  RowBuf buf[kDist + 1];
 #pragma unroll
-  for (int r0 = 0; r0 < kHaloH; r0 += kBatch) {
-    float4 a[kBatch][4];
+  for (int r = 0; r < kDist; ++r) issue_row(im, Cf4, south, it.pos[r], it.gi[r], buf[r]);
+#pragma unroll 1
+  for (int wc = 0; wc < n_w; ++wc) {
+    mbar_wait(bar_empty0 + 8u * sa, pha ^ 1);
+    const uint32_t a_stage = s_base + kOffA + sa * kAStageBytes;
+    const float4* __restrict__ im_c = im + wc * 4;
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      a[u][0] = a[u][1] = a[u][2] = a[u][3] = z;
-      if (it.gi[r0 + u] >= 0) {
-        const unsigned pos = (unsigned)it.pos[r0 + u];
-        const float4* __restrict__ north = im + (pos & kOffMask);
-        const bool e = (pos & kEastIn) != 0, sth = (pos & kSouthIn) != 0;
-        // ATen skips out-of-bounds taps (their weight is 0 anyway)
-        a[u][0] = ldg4(north);
-        if (e) a[u][1] = ldg4(north + Cf4);
-        if (sth) a[u][2] = ldg4(north + south);
-        if (e && sth) a[u][3] = ldg4(north + south + Cf4);
+    for (int r = 0; r < kHaloH; ++r) {
+      if (r + kDist < kHaloH)
+        issue_row(im_c, Cf4, south, it.pos[r + kDist], it.gi[r + kDist],
+                  buf[(r + kDist) % (kDist + 1)]);
+      else if (wc + 1 < n_w)
+        issue_row(im_c + 4, Cf4, south, it.pos[r + kDist - kHaloH], it.gi[r + kDist - kHaloH],
+                  buf[(r + kDist) % (kDist + 1)]);
+      if (active) {
+        const RowBuf& b = buf[r % (kDist + 1)];
+        const float4 v = blend4(b.a[0], b.a[1], b.a[2], b.a[3], s_wgt[r * kHaloW + col]);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
+                         item_dst(a_stage, ptid, r)),
+                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+        const int gi = it.gi[r];
+        if (ow != nullptr && gi >= 0 && (gi & kInterior))
+          st_streaming(ow + (long long)(gi & (kInterior - 1)) * Cf4 + wc * 4, v);
       }
     }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int r = r0 + u;
-      const float4 v =
-          blend4(a[u][0], a[u][1], a[u][2], a[u][3], s_wgt[r * kHaloW + (ptid >> 2)]);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(item_dst(a_stage, ptid, r)),
-                   "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                   : "memory");
-      const int gi = it.gi[r];
-      if (ow != nullptr && gi >= 0 && (gi & kInterior))
-        st_streaming(ow + (long long)(gi & (kInterior - 1)) * Cf4, v);
-    }
+    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+    mbar_arrive(bar_full0 + 8u * sa);
+    if (++sa == kStagesA) { sa = 0; pha ^= 1; }
   }
 }
 
@@ -442,24 +475,18 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
       producer_bar();
       Items items;
       load_items(items, ptid, s_pos, s_gidx);
-      for (int c = 0; c < p.n_chunks; ++c) {
+      // un-warped half of K: fire-and-forget copies
+      for (int c = 0; c < p.n_chunks_extra; ++c) {
         mbar_wait(bar_empty_a(sa), pha ^ 1);
-        const uint32_t a_stage = s_base + kOffA + sa * kAStageBytes;
-        bool is_extra;
-        const int slice = slice_of(c, p.n_chunks_extra, p.n_chunks - p.n_chunks_extra, &is_extra);
-        if (is_extra) {
-          fill_extra(p, t, slice, ptid, a_stage, items);
-          // arrive when this thread's copies have landed; the thread moves on
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
-                           bar_full_a(sa))
-                       : "memory");
-        } else {
-          fill_warped(p, t, slice, ptid, a_stage, s_wgt, items);
-          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-          mbar_arrive(bar_full_a(sa));
-        }
+        fill_extra(p, t, c, ptid, s_base + kOffA + sa * kAStageBytes, items);
+        // arrive when this thread's copies have landed; the thread moves on
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                         bar_full_a(sa))
+                     : "memory");
         if (++sa == kStagesA) { sa = 0; pha ^= 1; }
       }
+      // warped half of K
+      fill_warped_tile(p, t, ptid, s_base, bar_full_a(0), bar_empty_a(0), sa, pha, s_wgt, items);
     }
   } else if (warp < kProducerWarps + kEpilogueWarps) {
     // ===================== epilogue =====================
