@@ -171,6 +171,19 @@ except dvc.DvcError:
     pass
 dvc.unpatch()
 assert vm.flow_warp is stock
+# opt-in: every context warp fused into the conv that consumes it (tcgen05, inference)
+stock_mc = vm.DMC.motion_compensation
+dvc.patch(models, fuse_warp_conv=True)
+assert vm.DMC.motion_compensation is dvc.motion_compensation_fused
+net.eval()
+with torch.no_grad():
+    try:
+        net([torch.rand(1, 3, 64, 64), torch.rand(1, 3, 64, 64)])
+        raise SystemExit("expected DvcError on CPU tensors")
+    except dvc.DvcError:
+        pass
+dvc.unpatch()
+assert vm.DMC.motion_compensation is stock_mc
 print("ok")
 ''' % ROOT
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
