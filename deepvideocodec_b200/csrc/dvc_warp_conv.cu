@@ -100,8 +100,8 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kInterior = 1 << 30;  // gidx flag: the CTA owns this pixel of out_warp
 
 // instruction descriptor: D fp32, A/B TF32, both K-major, N = 64, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kCo >> 3) << 17) |
-                            ((kTileW >> 4) << 24);
+constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((kTileW >> 4) << 24);
+constexpr uint32_t kIdesc = kIdescBase | ((kCo >> 3) << 17);
 
 struct Params {
   const float* feat;
@@ -538,7 +538,7 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
     uint32_t tl = 0, pha = 0, phb = 0;
     int sa = 0, sb = 0;
     const uint32_t lbo_a = (uint32_t)kPlanePix * 16u, sbo_a = 128u;
-    const uint32_t lbo_b = (uint32_t)kCo * 16u, sbo_b = 128u;
+    const uint32_t lbo_b = 3u * (uint32_t)kCo * 16u, sbo_b = 128u;   // k-chunk planes of 192 rows
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
       const int buf = tl & 1;
       mbar_wait(bar_tempty(buf), ((tl >> 1) & 1) ^ 1);
@@ -553,17 +553,28 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
           tc_fence_after();
           if (elect_one_sync()) {
             const uint64_t b0 = make_desc(s_base + kOffB + sb * kBStageBytes, lbo_b, sbo_b);
+            // Row-tap fusion: halo row h (shifted by dx) is the A operand of every
+            // (output row r, tap row dy) with r + dy = h.  The accumulators of
+            // consecutive output rows are adjacent TMEM columns and the weights are
+            // packed [dx][k-chunk][dy = 2, 1, 0][co], so those up to three products are
+            // ONE tcgen05.mma with N = 64, 128 or 192: 18 instead of 36 per K-step, and
+            // the 4 KB A operand is read from shared memory half as often.
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              // descriptor start addresses advance in 16-byte units
-              const uint64_t bd = b0 + (uint64_t)(tap * 2 * kCo);
-              const uint32_t acc = (ks | tap) != 0 ? 1u : (uint32_t)(c != 0);
+            for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-              for (int r = 0; r < kRows; ++r) {
-                const uint64_t ad =
-                    a0 + (uint64_t)(ks * 2 * kPlanePix + (r + dy) * kHaloW + dx);
-                tc_mma_tf32(d0 + (uint32_t)(r * kCo), ad, bd, kIdesc, acc);
+              for (int i = 0; i < kHaloH; ++i) {
+                // the very first pass of a tile must not mix fresh and touched accumulators
+                // in one instruction: rows 0-2 via h = 2, row 3 via h = 5, then the rest
+                constexpr int first_order[kHaloH] = {2, 5, 0, 1, 3, 4};
+                const int h = first_order[i];
+                const int r_min = h - 2 > 0 ? h - 2 : 0, r_max = h < kRows - 1 ? h : kRows - 1;
+                const int n_rows = r_max - r_min + 1;
+                const int dy_max = h - r_min;                  // tap row of output row r_min
+                const uint64_t bd = b0 + (uint64_t)(dx * 2 * 3 * kCo + (2 - dy_max) * kCo);
+                const uint64_t ad = a0 + (uint64_t)(ks * 2 * kPlanePix + h * kHaloW + dx);
+                const uint32_t acc = (ks | dx) != 0 || i >= 2 ? 1u : (uint32_t)(c != 0);
+                tc_mma_tf32(d0 + (uint32_t)(r_min * kCo), ad, bd,
+                            kIdescBase | ((uint32_t)(n_rows * kCo >> 3) << 17), acc);
               }
             }
             tc_commit(bar_empty_b(sb));      // weight stage free when these MMAs retire
@@ -607,21 +618,26 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
 }
 
 // weight [Co=64, Ce+Cf, 3, 3] (element strides) ->
-//   [slice in consumption order][K-step 2][tap 9][k-chunk 2][co 64][4 channels]
+//   [slice in consumption order][K-step 2][dx 3][k-chunk 2][dy 2,1,0][co 64][4 channels]
 __global__ void pack_weights_kernel(const float* __restrict__ w, long long s_co, long long s_ci,
                                     long long s_ky, long long s_kx, float* __restrict__ out,
                                     int n_extra, int n_feat, int total) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int j = idx & 3, co = (idx >> 2) & 63, kc = (idx >> 8) & 1;
-  int rest = idx >> 9;
-  const int tap = rest % 9;
-  rest /= 9;
+  // [slice][K-step][dx 3][k-chunk 2][dy = 2, 1, 0][co 64][4 channels]
+  const int j = idx & 3, co = (idx >> 2) & 63;
+  int rest = idx >> 8;
+  const int dyi = rest % 3;
+  rest /= 3;
+  const int kc = rest & 1;
+  rest >>= 1;
+  const int kx = rest % 3;
+  rest /= 3;
   const int ks = rest & 1, c = rest >> 1;
   bool is_extra;
   const int slice = slice_of(c, n_extra, n_feat, &is_extra);
   const int ci = (is_extra ? 0 : n_extra * kChunk) + slice * kChunk + ks * 8 + kc * 4 + j;
-  const int ky = tap / 3, kx = tap - ky * 3;
+  const int ky = 2 - dyi;
   out[idx] = w[co * s_co + ci * s_ci + ky * s_ky + kx * s_kx];
 }
 
