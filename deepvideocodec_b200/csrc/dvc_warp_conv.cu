@@ -101,7 +101,6 @@ constexpr int kInterior = 1 << 30;  // gidx flag: the CTA owns this pixel of out
 
 // instruction descriptor: D fp32, A/B TF32, both K-major, N = 64, M = 128
 constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((kTileW >> 4) << 24);
-constexpr uint32_t kIdesc = kIdescBase | ((kCo >> 3) << 17);
 
 struct Params {
   const float* feat;
@@ -128,6 +127,18 @@ __host__ __device__ inline int slice_of(int c, int n_extra, int n_feat, bool* is
   *is_extra = c < n_extra;
   return c < n_extra ? c : c - n_extra;
 }
+
+#ifdef WC_PROFILE
+// cycle accounting of CTA 0 (debug builds only): [0] MMA wait-full in extra slices, [1] in
+// warped slices, [2] MMA total, [3] producer wait-empty extra, [4] warped, [5] producer fill
+// time of warped slices (acquire -> arrive), [6] producer total, [7] taps phase
+__device__ unsigned long long g_wc_prof[8];
+#define WC_T0() const long long _t0 = clock64()
+#define WC_ACC(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_wc_prof[i], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define WC_T0()
+#define WC_ACC(i)
+#endif
 
 // ---- PTX wrappers ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -326,6 +337,65 @@ __device__ __forceinline__ void fill_extra(const Params& p, const Tile& t, int c
 // latency but needs 48 registers of tap data: with 736 threads the cap is 80
 // registers and the spills cost more than the latency (measured 777 us at
 // distance 1, 885 us at distance 2; batches without pipelining 801 us).
+// The un-warped half of K for one tile.  cp.async (LDGSTS) straight into the
+// stage looked ideal and was the bottleneck of this phase: the LSU throttles it
+// to ~21 B/clk per SM with this 16-bytes-per-lane pattern, and a slice could only
+// be requested after its stage had been released, so the tensor core waited for a
+// third of the phase (in-kernel cycle accounting, tools/_wc_prof.py).  Plain
+// LDG.128 reach 2.3x that rate, and a row costs only 4 registers here, so the
+// copy is a register pipeline a whole slice deep: the 6 rows of slice c + 1 are
+// in flight while slice c is stored, the loads do not wait for the stage (only
+// the STS do), and when the stage frees up the data is already in registers.
+__device__ __forceinline__ float4 ldg4_stream(const float4* p) {
+  float4 v;   // read-once data: do not take L1 lines away from the tap gathers
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void fill_extra_tile(const Params& p, const Tile& t, int ptid,
+                                                uint32_t s_base, uint32_t bar_full0,
+                                                uint32_t bar_empty0, int& sa, uint32_t& pha,
+                                                const Items& it) {
+  const int n_e = p.n_chunks_extra;
+  if (n_e <= 0) return;
+  const int Ce4 = p.Ce >> 2;
+  const float4* __restrict__ ex = reinterpret_cast<const float4*>(p.extra) +
+                                  (long long)t.n * p.H * p.W * Ce4 + (ptid & 3);
+  const bool active = ptid < kFillThreads;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* src[kHaloH];
+#pragma unroll
+  for (int r = 0; r < kHaloH; ++r)
+    src[r] = ex + (it.gi[r] >= 0 ? (long long)(it.gi[r] & (kInterior - 1)) * Ce4 : 0);
+  const uint32_t t_off = (uint32_t)((ptid & 3) * kPlanePix + (ptid >> 2)) * 16u;
+  float4 v[kHaloH];
+#pragma unroll
+  for (int r = 0; r < kHaloH; ++r) v[r] = it.gi[r] >= 0 ? ldg4_stream(src[r]) : z;
+#pragma unroll 1
+  for (int c = 0; c < n_e; ++c) {
+    { WC_T0(); mbar_wait(bar_empty0 + 8u * sa, pha ^ 1); if (ptid < 32) WC_ACC(3); }
+    const uint32_t dst = s_base + kOffA + sa * kAStageBytes + t_off;
+#pragma unroll
+    for (int r = 0; r < kHaloH; ++r) {
+      if (active)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
+                         dst + (uint32_t)(r * kHaloW * 16)),
+                     "f"(v[r].x), "f"(v[r].y), "f"(v[r].z), "f"(v[r].w)
+                     : "memory");
+      // outside the image: zeros (the conv's zero padding)
+      if (c + 1 < n_e) v[r] = it.gi[r] >= 0 ? ldg4_stream(src[r] + (c + 1) * 4) : z;
+    }
+    // generic-proxy stores -> visible to the tensor core's async proxy; ONE arrival per
+    // warp (544 per-thread arrivals on one mbarrier serialise for over a microsecond)
+    fence_proxy_async();
+    __syncwarp();
+    if ((ptid & 31) == 0) mbar_arrive(bar_full0 + 8u * sa);
+    if (++sa == kStagesA) { sa = 0; pha ^= 1; }
+  }
+}
+
 #ifndef WC_DIST
 #define WC_DIST 1
 #endif
@@ -383,7 +453,8 @@ __device__ __forceinline__ void fill_warped_tile(const Params& p, const Tile& t,
   for (int r = 0; r < kDist; ++r) issue_row(im, Cf4, south, it.pos[r], it.gi[r], buf[r]);
 #pragma unroll 1
   for (int wc = 0; wc < n_w; ++wc) {
-    mbar_wait(bar_empty0 + 8u * sa, pha ^ 1);
+    { WC_T0(); mbar_wait(bar_empty0 + 8u * sa, pha ^ 1); if (ptid < 32) WC_ACC(4); }
+    WC_T0();
     const uint32_t a_stage = s_base + kOffA + sa * kAStageBytes;
     const float4* __restrict__ im_c = im + wc * 4;
 #pragma unroll
@@ -406,8 +477,12 @@ __device__ __forceinline__ void fill_warped_tile(const Params& p, const Tile& t,
           st_streaming(ow + (long long)(gi & (kInterior - 1)) * Cf4 + wc * 4, v);
       }
     }
-    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-    mbar_arrive(bar_full0 + 8u * sa);
+    // generic-proxy stores -> visible to the tensor core's async proxy; ONE arrival per
+    // warp (544 per-thread arrivals on one mbarrier serialise for over a microsecond)
+    fence_proxy_async();
+    __syncwarp();
+    if ((ptid & 31) == 0) mbar_arrive(bar_full0 + 8u * sa);
+    if (ptid < 32) WC_ACC(5);
     if (++sa == kStagesA) { sa = 0; pha ^= 1; }
   }
 }
@@ -435,7 +510,7 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
   if (warp == kProducerWarps + kEpilogueWarps) {
     if (lane == 0) {
       for (int s = 0; s < kStagesA; ++s) {
-        mbar_init(bar_full_a(s), kProducerThreads);
+        mbar_init(bar_full_a(s), kProducerWarps);
         mbar_init(bar_empty_a(s), 1);                // tcgen05.commit
       }
       for (int s = 0; s < kStagesB; ++s) {
@@ -468,26 +543,28 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
     int* s_gidx = reinterpret_cast<int*>(smem + kOffGidx);
     int sa = 0;
     uint32_t pha = 0;
+#ifdef WC_PROFILE
+    const long long _role_t0 = clock64();
+#endif
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const Tile t = tile_of(p, tile);
-      producer_bar();  // everyone is done with the previous tile's tap records
-      compute_taps(p, t, ptid, s_wgt, s_pos, s_gidx);
-      producer_bar();
+      {
+        WC_T0();
+        producer_bar();  // everyone is done with the previous tile's tap records
+        compute_taps(p, t, ptid, s_wgt, s_pos, s_gidx);
+        producer_bar();
+        if (warp == 0) WC_ACC(7);
+      }
       Items items;
       load_items(items, ptid, s_pos, s_gidx);
-      // un-warped half of K: fire-and-forget copies
-      for (int c = 0; c < p.n_chunks_extra; ++c) {
-        mbar_wait(bar_empty_a(sa), pha ^ 1);
-        fill_extra(p, t, c, ptid, s_base + kOffA + sa * kAStageBytes, items);
-        // arrive when this thread's copies have landed; the thread moves on
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
-                         bar_full_a(sa))
-                     : "memory");
-        if (++sa == kStagesA) { sa = 0; pha ^= 1; }
-      }
+      // un-warped half of K
+      fill_extra_tile(p, t, ptid, s_base, bar_full_a(0), bar_empty_a(0), sa, pha, items);
       // warped half of K
       fill_warped_tile(p, t, ptid, s_base, bar_full_a(0), bar_empty_a(0), sa, pha, s_wgt, items);
     }
+#ifdef WC_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_wc_prof[6], (unsigned long long)(clock64() - _role_t0));
+#endif
   } else if (warp < kProducerWarps + kEpilogueWarps) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -537,6 +614,9 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
     // ===================== MMA issuer =====================
     uint32_t tl = 0, pha = 0, phb = 0;
     int sa = 0, sb = 0;
+#ifdef WC_PROFILE
+    const long long _role_t0 = clock64();
+#endif
     const uint32_t lbo_a = (uint32_t)kPlanePix * 16u, sbo_a = 128u;
     const uint32_t lbo_b = 3u * (uint32_t)kCo * 16u, sbo_b = 128u;   // k-chunk planes of 192 rows
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tl) {
@@ -545,7 +625,7 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(buf * (kRows * kCo));
       for (int c = 0; c < p.n_chunks; ++c) {
-        mbar_wait(bar_full_a(sa), pha);
+        { WC_T0(); mbar_wait(bar_full_a(sa), pha); WC_ACC(c < p.n_chunks_extra ? 0 : 1); }
         const uint64_t a0 = make_desc(s_base + kOffA + sa * kAStageBytes, lbo_a, sbo_a);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -589,6 +669,9 @@ warp_conv3x3_kernel(const __grid_constant__ Params p) {
         if (++sa == kStagesA) { sa = 0; pha ^= 1; }
       }
     }
+#ifdef WC_PROFILE
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_wc_prof[2], (unsigned long long)(clock64() - _role_t0));
+#endif
   } else {
     // ===================== weight loader =====================
     if (lane == 0) {
@@ -645,6 +728,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, long long s_co,
 }  // namespace dvc
 
 using namespace dvc;
+
+#ifdef WC_PROFILE
+extern "C" int dvc_debug_warp_conv_profile(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, wc::g_wc_prof, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(wc::g_wc_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int64_t dvc_conv3x3_packed_weight_floats(int64_t Co, int64_t Ci) {
   if (Co != wc::kCo || Ci <= 0 || Ci % wc::kChunk) return 0;
