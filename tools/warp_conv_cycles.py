@@ -1,3 +1,5 @@
+"""In-kernel cycle accounting of the fused warp + conv kernel (CTA 0): who waits for whom.
+Needs a profiling build:  nvcc ... -DWC_PROFILE -o deepvideocodec_b200/libdvc_prof.so csrc/dvc_*.cu"""
 import os, sys, ctypes, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.environ["DVC_B200_LIB"] = os.path.join(ROOT, "deepvideocodec_b200", "libdvc_prof.so")
