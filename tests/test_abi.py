@@ -23,7 +23,8 @@ def test_header_cites_reference_interfaces():
     import deepvideocodec_b200._native as nat
     text = open(os.path.join(nat.INCLUDE_DIR, "dvc_b200.h")).read()
     for cite in ("layers.py:175-198", "layers.py:201-206", "video_model.py:497-504",
-                 "utils.py:149-152", "video_model.py:176-189", "train.py:74-93"):
+                 "utils.py:149-152", "video_model.py:176-189", "train.py:74-93",
+                 "video_model.py:55-61", "video_model.py:502-504"):
         assert cite in text, cite
     assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S).lower()
 
@@ -51,6 +52,20 @@ def test_invalid_arguments_fail_without_launching():
     assert rc == -1 and b"multiples of 4" in lib.dvc_last_error_string()
     rc = lib.dvc_rate_finalize(1, 4, 1, 0.0, None, None, None, None)
     assert rc == -1
+    # fused warp + 3x3 conv (row f3): every shape rule is checked before the launch
+    a = 0x1000                      # 16-byte aligned, never dereferenced
+    call = lambda **k: lib.dvc_warp_conv3x3_fwd(   # noqa: E731
+        k.get("feat", a), a, k.get("extra", a), a, None, a, a, 1, k.get("cf", 64), k.get("ce", 64),
+        k.get("co", 64), 16, 128, st, k.get("level", 0), 0, None)
+    assert call(co=32) == -1 and b"Co must be 64" in lib.dvc_last_error_string()
+    assert call(cf=24) == -1 and b"multiple of 16" in lib.dvc_last_error_string()
+    assert call(ce=8) == -1 and b"multiple of 16" in lib.dvc_last_error_string()
+    assert call(extra=None) == -1 and b"mismatch" in lib.dvc_last_error_string()
+    assert call(feat=a + 4) == -1 and b"aligned" in lib.dvc_last_error_string()
+    assert call(level=3) == -1 and b"flow_downscale" in lib.dvc_last_error_string()
+    assert lib.dvc_conv3x3_packed_weight_floats(64, 128) == 128 * 9 * 64
+    assert lib.dvc_conv3x3_packed_weight_floats(32, 128) == 0
+    assert lib.dvc_conv3x3_pack_weights(a, st, 64, 64, 40, a, None) == -1
 
 
 def test_library_is_sm100a_only():
