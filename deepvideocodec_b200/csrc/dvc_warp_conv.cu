@@ -132,7 +132,7 @@ __host__ __device__ inline int slice_of(int c, int n_extra, int n_feat, bool* is
 // cycle accounting of CTA 0 (debug builds only): [0] MMA wait-full in extra slices, [1] in
 // warped slices, [2] MMA total, [3] producer wait-empty extra, [4] warped, [5] producer fill
 // time of warped slices (acquire -> arrive), [6] producer total, [7] taps phase
-__device__ unsigned long long g_wc_prof[8];
+__device__ unsigned long long g_wc_prof[12];
 #define WC_T0() const long long _t0 = clock64()
 #define WC_ACC(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_wc_prof[i], (unsigned long long)(clock64() - _t0)); } while (0)
 #else
@@ -377,6 +377,8 @@ __device__ __forceinline__ void fill_extra_tile(const Params& p, const Tile& t, 
   for (int c = 0; c < n_e; ++c) {
     { WC_T0(); mbar_wait(bar_empty0 + 8u * sa, pha ^ 1); if (ptid < 32) WC_ACC(3); }
     const uint32_t dst = s_base + kOffA + sa * kAStageBytes + t_off;
+    {
+    WC_T0();
 #pragma unroll
     for (int r = 0; r < kHaloH; ++r) {
       if (active)
@@ -387,11 +389,21 @@ __device__ __forceinline__ void fill_extra_tile(const Params& p, const Tile& t, 
       // outside the image: zeros (the conv's zero padding)
       if (c + 1 < n_e) v[r] = it.gi[r] >= 0 ? ldg4_stream(src[r] + (c + 1) * 4) : z;
     }
+    if (ptid < 32) WC_ACC(8);
+    }
     // generic-proxy stores -> visible to the tensor core's async proxy; ONE arrival per
     // warp (544 per-thread arrivals on one mbarrier serialise for over a microsecond)
+    {
+    WC_T0();
     fence_proxy_async();
+    if (ptid < 32) WC_ACC(9);
+    }
+    {
+    WC_T0();
     __syncwarp();
     if ((ptid & 31) == 0) mbar_arrive(bar_full0 + 8u * sa);
+    if (ptid < 32) WC_ACC(10);
+    }
     if (++sa == kStagesA) { sa = 0; pha ^= 1; }
   }
 }
@@ -732,9 +744,9 @@ using namespace dvc;
 #ifdef WC_PROFILE
 extern "C" int dvc_debug_warp_conv_profile(unsigned long long* out8, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, wc::g_wc_prof, sizeof(unsigned long long) * 8);
+  cudaMemcpyFromSymbol(out8, wc::g_wc_prof, sizeof(unsigned long long) * 12);
   if (reset) {
-    unsigned long long z[8] = {0};
+    unsigned long long z[12] = {0};
     cudaMemcpyToSymbol(wc::g_wc_prof, z, sizeof(z));
   }
   return 0;

@@ -17,7 +17,7 @@ flow = lp / lp.std() * 4.0
 weight = torch.randn(64, 128, 3, 3, device=dev) * 0.05
 bias = torch.randn(64, device=dev)
 fn = nat.lib().dvc_debug_warp_conv_profile
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 12)()
 with torch.no_grad():
     for _ in range(3):
         layers.warp_conv3x3(feat, flow, weight, bias, extra)
@@ -25,7 +25,8 @@ with torch.no_grad():
     layers.warp_conv3x3(feat, flow, weight, bias, extra)
     fn(buf, 1)
 names = ["mma wait-full (extra slices)", "mma wait-full (warped slices)", "mma total", "producer wait-empty (extra)",
-         "producer wait-empty (warped)", "producer fill warped (acquire->arrive)", "producer total", "taps phase"]
+         "producer wait-empty (warped)", "producer fill warped (acquire->arrive)", "producer total", "taps phase",
+         "extra: STS + LDG issue", "extra: fence.proxy.async", "extra: syncwarp + arrive", "-"]
 tot = buf[2]
 for n, v in zip(names, buf):
     print(f"{n:42s} {v:12d} clk  {100.0 * v / max(tot, 1):5.1f} % of the MMA role's time")
