@@ -302,9 +302,12 @@ warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
 #define DVC_PLANAR_VERT 1   // a thread's two pixels are rows h, h + 8 of a 32 x 16 tile (0: columns w, w + 32 of a 64 x 8
                             // tile: wider boxes, measured 6-27 % slower on rough flows, equal on gentle ones)
 #endif
-constexpr int kPlPx = 2;                              // pixels per thread
-constexpr int kPlTileW = DVC_PLANAR_VERT ? 32 : 64, kPlTileH = DVC_PLANAR_VERT ? 16 : 8;
-constexpr int kPlBoxW4 = DVC_PLANAR_VERT ? 18 : 28, kPlBoxH = DVC_PLANAR_VERT ? 40 : 26;   // staged box limits
+#ifndef DVC_PLANAR_PX   // 3 / 4 pixels per thread (taller tiles): 3-5 % faster on gentle flows, 5-100 %
+#define DVC_PLANAR_PX 2 // slower on rough ones (fewer tiles fit their box) -- measured, 2 kept
+#endif
+constexpr int kPlPx = DVC_PLANAR_PX;                  // pixels per thread
+constexpr int kPlTileW = DVC_PLANAR_VERT ? 32 : 32 * kPlPx, kPlTileH = DVC_PLANAR_VERT ? 8 * kPlPx : 8;
+constexpr int kPlBoxW4 = DVC_PLANAR_VERT ? 18 : 28, kPlBoxH = DVC_PLANAR_VERT ? 8 * kPlPx + 24 : 26;   // staged box limits
 constexpr int kPlBufFloats = kPlBoxW4 * 4 * kPlBoxH;  // 2912 floats = 11648 B
 #ifndef DVC_PLANAR_BUFS
 #define DVC_PLANAR_BUFS 4
@@ -317,8 +320,11 @@ constexpr int kPlSmemBytes = kPlBufs * kPlBufFloats * 4;
 // kStaged = false: the complementary launch (no shared memory -> all of L1 for the
 //                  incoherent gathers) takes the tiles the first one left, others return.
 // Both evaluate the same deterministic box test, so no flag buffer is needed.
+#ifndef DVC_PLANAR_MINB
+#define DVC_PLANAR_MINB 4
+#endif
 template <bool kStaged>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, DVC_PLANAR_MINB)
 warp_planar_kernel(const __grid_constant__ WarpTask t) {
   extern __shared__ __align__(16) float pl_smem[];
   __shared__ int s_red[32];   // static: the gather launch has no dynamic shared memory
@@ -499,6 +505,12 @@ static int launch_planar(WarpTask t, const dvc_warp_task& in, cudaStream_t strea
   t.tiles_y = (int)((in.H + kPlTileH - 1) / kPlTileH);
   const long long nb = (long long)t.tiles_x * t.tiles_y * in.N;
   DVC_REQUIRE(nb < 2147483647LL, "flow_warp: too many tiles");
+  if (kPlSmemBytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(warp_planar_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmemBytes);
+    if (e != cudaSuccess)
+      return fail(DVC_ERR_CUDA, "flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
   warp_planar_kernel<true><<<(unsigned)nb, kThreads, kPlSmemBytes, stream>>>(t);
   int rc = check_launch("warp_planar_kernel<staged>");
   if (rc) return rc;
