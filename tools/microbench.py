@@ -69,6 +69,23 @@ with torch.no_grad():
                                  "eager_cuda_us": te * 1e3, "bit_identical_to_eager": bool(ok)})
             del ims, flows
             torch.cuda.empty_cache()
+    # SpyNet's four 3-channel warps of a 1080p P-frame (layers.py:261; SURVEY.md 8d "optional second
+    # figure", 88.78 MB): per-op launches (what the patched ME_Spynet does) and one warp_multi launch
+    sp = [(136, 240), (272, 480), (544, 960), (1088, 1920)]
+    sets = [[(torch.rand(1, 3, h, w, device=dev, generator=g), smooth_flow(h, w, g)) for h, w in sp]
+            for _ in range(6)]
+    alg = sum(4 * h * w * 8 for h, w in sp)
+    t = timeit([(lambda s=s: [dvc.flow_warp(im, fl) for im, fl in s]) for s in sets])
+    tm = timeit([(lambda s=s: dvc.warp_multi(s)) for s in sets])
+    te = timeit([(lambda s=s: [dmc_ref.flow_warp(im, fl) for im, fl in s]) for s in sets], 10, 3)
+    out["cases"].append({"op": "SpyNet warps x4 (3 ch, 136x240 .. 1088x1920)", "shape": [4, 3, 1088, 1920],
+                         "layout": "nchw", "algorithmic_MB": alg / 1e6, "us": t * 1e3,
+                         "us_one_launch": tm * 1e3, "GBps": alg / tm / 1e6,
+                         "frac_of_measured_peak": alg / tm / 1e6 / PEAK, "eager_cuda_us": te * 1e3,
+                         "bit_identical_to_eager": bool(all(
+                             torch.equal(a, dmc_ref.flow_warp(im, fl))
+                             for a, (im, fl) in zip(dvc.warp_multi(sets[0]), sets[0])))})
+    del sets
     # Gaussian conditional, 192 ch x 136 x 240 (module boundary: 20 B/element)
     oem = _oracle_entropy_models()
     n_el = 192 * 136 * 240
