@@ -24,7 +24,26 @@ import torch
 from . import _native as nat
 from .entropy_models import _packed_cached
 
-__all__ = ["PFramePath", "synthetic_pframe_inputs", "pframe_algorithmic_bytes"]
+__all__ = ["PFramePath", "synthetic_pframe_inputs", "pframe_algorithmic_bytes", "DPB_KEYS",
+           "frame_keys", "SpyNetWarps", "spynet_algorithmic_bytes"]
+
+# What the codec keeps on the device between frames: the decoded picture buffer
+# (``dpb``, video_model.py:529-534, 544-549).  ``x_ref`` is the previous
+# reconstruction, ``feat1..3`` are the feature pyramid extracted from
+# ``dpb["feature_ref"]`` (video_model.py:490-504).  Everything else a P-frame
+# of the path consumes depends on the NEW frame (motion field, latents, priors).
+DPB_KEYS = ("x_ref", "feat1", "feat2", "feat3")
+
+
+def frame_keys(inputs):
+    """Input keys that change with every new frame (everything but the dpb)."""
+    return tuple(k for k in inputs if k not in DPB_KEYS)
+
+
+def spynet_algorithmic_bytes(h, w, n=1):
+    """The four 3-channel warps of ``ME_Spynet.forward`` (layers.py:261) at
+    H/8, H/4, H/2, H: SURVEY.md 8d's optional second figure (88.78 MB at 1080p)."""
+    return sum(4 * n * (h >> k) * (w >> k) * (2 * 3 + 2) for k in range(4))
 
 
 def pframe_algorithmic_bytes(h, w, n=1, c_feat=64, c_mv=64, c_y=96, c_z=64):
@@ -51,16 +70,20 @@ def pframe_algorithmic_bytes(h, w, n=1, c_feat=64, c_mv=64, c_y=96, c_z=64):
 
 
 def synthetic_pframe_inputs(h, w, device, seed, n=1, regime="smooth", c_feat=64, c_mv=64,
-                            c_y=96, c_z=64):
+                            c_y=96, c_z=64, layout="channels_last"):
     """Synthetic tensors of SURVEY.md 8d config 2 (shapes of a random-init DMC
     at H x W; values from the controlled distributions, not the degenerate
-    random-init activations).  Features are channels_last (the fast path)."""
+    random-init activations).  ``layout``: memory format of the three feature
+    scales -- ``channels_last`` (the fast path) or ``nchw`` (what the stock
+    reference allocates); values are identical in both."""
     g = torch.Generator(device=device).manual_seed(seed)
 
     def randn(*s):
         return torch.randn(*s, device=device, generator=g)
 
-    cl = torch.channels_last
+    if layout not in ("channels_last", "nchw"):
+        raise ValueError(layout)
+    cl = torch.channels_last if layout == "channels_last" else torch.contiguous_format
     inp = {"x_ref": torch.rand(n, 3, h, w, device=device, generator=g)}
     inp["feat1"] = randn(n, c_feat, h, w).contiguous(memory_format=cl)
     inp["feat2"] = randn(n, c_feat, h // 2, w // 2).contiguous(memory_format=cl)
@@ -98,8 +121,14 @@ class PFramePath:
     LABELS = ("motion", "frame")
 
     def __init__(self, inputs, eb_modules, gc_bounds=(0.11, 1e-9), num_pixels=None,
-                 materialize_pyramid=False):
+                 materialize_pyramid=False, outputs=None):
+        """``outputs``: optional preallocated tensors for ``warpframe`` /
+        ``context1..3`` (same shape and memory format as the matching input).  A
+        GOP runner passes the *next* frame's dpb buffers here, so the warped
+        frame and contexts of frame t are written straight into the reference
+        slots of frame t + 1 (no copy; ``deepvideocodec_b200.gop``)."""
         self.inp = inputs
+        outputs = outputs or {}
         # mv2 / mv3 are only intermediates of DMC.motion_compensation
         # (video_model.py:499-500); by default they are derived inside the warp
         # kernel and never written to HBM
@@ -115,9 +144,19 @@ class PFramePath:
         o = {}
         o["mv2"] = torch.empty((n, 2, h // 2, w // 2), device=dev)
         o["mv3"] = torch.empty((n, 2, h // 4, w // 4), device=dev)
-        o["warpframe"] = torch.empty_like(x_ref)
+        def out_like(name, like):
+            t = outputs.get(name)
+            if t is None:
+                return torch.empty_like(like)
+            if t.shape != like.shape or t.stride() != like.stride() or t.dtype != like.dtype \
+                    or t.device != like.device:
+                raise nat.DvcError(f"PFramePath: outputs[{name!r}] must match its input's "
+                                   "shape, strides, dtype and device")
+            return t
+
+        o["warpframe"] = out_like("warpframe", x_ref)
         for k in (1, 2, 3):
-            o[f"context{k}"] = torch.empty_like(inputs[f"feat{k}"])
+            o[f"context{k}"] = out_like(f"context{k}", inputs[f"feat{k}"])
         # [4 likelihood tensors][N] ln-sums: motion.y, motion.z, frame.y, frame.z (dict order
         # of the reference's likelihood dicts, video_model.py:233, 577-579)
         o["logsums"] = torch.zeros((4, n), dtype=torch.float64, device=dev)
@@ -195,14 +234,22 @@ class PFramePath:
                          None, None, None, None, P(ls_y), P(self._ws[2 * li]), n, c, lh, lw,
                          keep(st(y)), keep(st(mu)), keep(st(sg)), keep(st(prior)), None,
                          keep(st(yh)), None, self._sb, self._lb)))
-        ent.append((L.dvc_rate_finalize, "dvc_rate_finalize",
-                    (P(o["logsums"]), 4, n, self.num_pixels, P(o["bpp"]), P(o["bpp_total"]),
-                     P(o["bits"]))))
+        self._fin_head = (P(o["logsums"]), 4, n, self.num_pixels, P(o["bpp"]), P(o["bpp_total"]))
+        self._fin_bits = P(o["bits"])
         self._pre_calls = calls
         self._ent_calls = ent
 
-    def launch(self, warp_events=None, concurrent=True):
+    def _finalize(self, stream, bits_ptr):
+        rc = self._lib.dvc_rate_finalize(*self._fin_head, bits_ptr or self._fin_bits, stream)
+        if rc:
+            nat.check(rc, "dvc_rate_finalize")
+
+    def launch(self, warp_events=None, concurrent=True, bits_ptr=None):
         """Enqueue the P-frame on the current stream of ``self.device``.
+
+        ``bits_ptr``: device address of ``N`` fp64 words that receive this frame's
+        bits instead of ``out["bits"]`` (a GOP runner points it at row t of a
+        per-unit table, so no frame needs a host read).
 
         The motion-compensation branch (one launch) and the entropy branch (six
         small launches + the rate finalise) are independent given the conv
@@ -224,6 +271,7 @@ class PFramePath:
                 rc = fn(*args, s2)
                 if rc:
                     nat.check(rc, name)
+            self._finalize(s2, bits_ptr)
             self._join.record(side)
         for fn, name, args in self._pre_calls:
             rc = fn(*args, s)
@@ -244,6 +292,7 @@ class PFramePath:
                 rc = fn(*args, s)
                 if rc:
                     nat.check(rc, name)
+            self._finalize(s, bits_ptr)
         return self.out
 
     _side = {}
@@ -262,4 +311,47 @@ class PFramePath:
 
     @property
     def n_launches(self):
-        return len(self._pre_calls) + 1 + len(self._ent_calls)
+        """Kernel launches of one ``launch()``.  NCHW (non channels_last) feature
+        scales take the staged planar path: two launches per scale (the staged
+        tiles and their complement) instead of a share of the one multi-scale
+        launch."""
+        planar = sum(1 for k in (1, 2, 3)
+                     if self.inp[f"feat{k}"].is_contiguous() and self.inp[f"feat{k}"].size(1) >= 8)
+        return len(self._pre_calls) + 1 + 2 * planar + len(self._ent_calls) + 1
+
+
+class SpyNetWarps:
+    """The four 3-channel warps of ``ME_Spynet.forward`` (layers.py:242-264, the
+    ``flow_warp(im2_list[level], flow_up)`` at :261) as ONE launch: SURVEY.md 8d's
+    optional second figure.  Inputs are synthetic pyramids of the reference frame
+    and flows of the matching sizes (in the codec each level's flow depends on
+    the previous level's conv output, so the four warps cannot be one launch
+    there; this measures their cost, not a drop-in)."""
+
+    def __init__(self, h, w, device, seed, n=1):
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.ims, self.flows, self.outs = [], [], []
+        tasks = (nat.WarpTask * 4)()
+        self._keep = [tasks]
+        for k in range(4):
+            hh, ww = h >> (3 - k), w >> (3 - k)
+            im = torch.rand(n, 3, hh, ww, device=device, generator=g)
+            f = torch.randn(n, 2, hh, ww, device=device, generator=g)
+            f = torch.nn.functional.avg_pool2d(f, 15, stride=1, padding=7, count_include_pad=False)
+            flow = (f / f.std() * 2.0).contiguous()
+            out = torch.empty_like(im)
+            t = tasks[k]
+            t.im, t.flow, t.out = im.data_ptr(), flow.data_ptr(), out.data_ptr()
+            t.N, t.C, t.H, t.W = im.shape
+            t.im_st, t.flow_st, t.out_st = nat.st4(im), nat.st4(flow), nat.st4(out)
+            t.flow_downscale = 0
+            self.ims.append(im), self.flows.append(flow), self.outs.append(out)
+        self._args = (ctypes.cast(tasks, ctypes.c_void_p), 4, 0)
+        self.device = device
+        self.bytes = spynet_algorithmic_bytes(h, w, n)
+
+    def launch(self):
+        rc = nat.lib().dvc_warp_multi_fwd(*self._args,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            nat.check(rc, "dvc_warp_multi_fwd")

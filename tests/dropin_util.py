@@ -88,14 +88,30 @@ def frames(n_frames, batch, h, w, device, seed=0, channels_last=False):
 def capture_latents(model):
     """Forward hooks recording the quantised latents ``y_hat`` of both context
     models (first return value of their ``forward``)."""
-    store = {"motion": [], "frame": []}
+    store = {"motion": [], "frame": [], "motion.z": [], "frame.z": []}
     hooks = [
         model.motion_context_model.register_forward_hook(
             lambda m, i, o: store["motion"].append(o[0].detach())),
         model.frame_context_model.register_forward_hook(
             lambda m, i, o: store["frame"].append(o[0].detach())),
     ]
+    # hyper-latents z: input of hyper_decoder is z_hat; z itself is the hyper-encoder output
+    hooks += [
+        model.motion_context_model.hyper_encoder.register_forward_hook(
+            lambda m, i, o: store["motion.z"].append(o.detach())),
+        model.frame_context_model.hyper_encoder.register_forward_hook(
+            lambda m, i, o: store["frame.z"].append(o.detach())),
+    ]
     return store, hooks
+
+
+def eb_likelihood_fp64(eb, z):
+    """The factorised-bottleneck likelihood of ``z`` evaluated in fp64 with the
+    eager restatement (the value both fp32 implementations approximate)."""
+    import copy
+    eb64 = copy.deepcopy(eb).double().eval()
+    with torch.no_grad():
+        return eb64(z.double())[1]
 
 
 def run_forward(model, fr, seed=None, grad=False):
@@ -127,8 +143,13 @@ def stock_collect():
     return _stock_collect
 
 
-def compare_forward(out_s, lat_s, out_p, lat_p, num_pixels):
-    """Error summary of one stock-vs-patched ``DMC.forward``."""
+def compare_forward(out_s, lat_s, out_p, lat_p, num_pixels, stock=None):
+    """Error summary of one stock-vs-patched ``DMC.forward``.  With ``stock``
+    (eval mode only) the z likelihoods of both arms are also compared with the
+    fp64 evaluation of the same formula: eager's own fp32 rounding order in the
+    bottleneck's last matmul changes with the tensor size
+    (profiles/r02_eb_probe.json), so at small sizes neither arm is "the" fp32
+    result and the distance to fp64 is the meaningful yardstick."""
     import deepvideocodec_b200 as dvc
     rep = {"frames": []}
     for i, (xs, xp) in enumerate(zip(out_s["x_hat"], out_p["x_hat"])):
@@ -144,6 +165,13 @@ def compare_forward(out_s, lat_s, out_p, lat_p, num_pixels):
                 lp = out_p["likelihoods"][i][label][field]
                 fr[f"{label}.{field}_lik_max_rel"] = rel_err(lp, ls)
                 fr[f"{label}.{field}_floor_frac"] = (ls <= 1e-9).float().mean().item()
+            if stock is not None:
+                cm = stock.motion_context_model if label == "motion" else stock.frame_context_model
+                z = lat_s[f"{label}.z"][i]
+                fr[f"{label}.z_equal_inputs"] = bool(torch.equal(z, lat_p[f"{label}.z"][i]))
+                l64 = eb_likelihood_fp64(cm.entropy_bottleneck, z)
+                fr[f"{label}.z_lik_stock_vs_fp64"] = rel_err(out_s["likelihoods"][i][label]["z"], l64)
+                fr[f"{label}.z_lik_patched_vs_fp64"] = rel_err(out_p["likelihoods"][i][label]["z"], l64)
         rep["frames"].append(fr)
     bs, ds = stock_collect()(out_s["likelihoods"], num_pixels)
     bp, dp = dvc.collect_likelihoods_list(out_p["likelihoods"], num_pixels)

