@@ -118,6 +118,32 @@ def load_stock_and_patched(**patch_kwargs):
     return stock, patched
 
 
+def load_reference_train_ns(names):
+    """Several top-level definitions of ``dmc/train.py`` executed into ONE scratch
+    namespace (so ``RateDistortionLoss`` finds ``collect_likelihoods_list``);
+    returned as a ``types.SimpleNamespace`` -- a stand-in for the ``train`` module
+    that ``deepvideocodec_b200.patch(models, train_module=ns)`` can rebind."""
+    import ast
+    import math
+    import types
+    from collections import defaultdict
+    from typing import List
+
+    import torch
+    path = os.path.join(find_reference_root() or REFERENCE_ROOT, "dmc", "train.py")
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    missing = set(names) - {n.name for n in body}
+    if missing:
+        raise KeyError(sorted(missing))
+    mod = types.ModuleType("dvc_ref_train_ns")
+    mod.__dict__.update({"torch": torch, "nn": torch.nn, "optim": torch.optim, "math": math,
+                         "defaultdict": defaultdict, "List": List})
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), mod.__dict__)
+    return mod
+
+
 def load_reference_train_fn(name):
     """Fetch one function from ``dmc/train.py`` *without importing the module*
     (importing it overwrites CUDA_VISIBLE_DEVICES, train.py:43, and pulls in
