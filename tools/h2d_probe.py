@@ -27,7 +27,7 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SIZES_MB = (8, 44, 256, 768)
+SIZES_MB = (44, 256)
 
 
 def topology(local):
@@ -108,7 +108,8 @@ def main():
     rows = []
     for variant in ("default", "bound", "streams2"):
         if variant == "bound":
-            if not cpus:
+            if not cpus or (topo.get("numa_nodes") or 1) <= 1:
+                topo["bound_skipped"] = "one NUMA node visible: nothing to bind to"
                 continue
             try:
                 os.sched_setaffinity(0, cpus)
