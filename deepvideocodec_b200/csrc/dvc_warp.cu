@@ -17,6 +17,7 @@
 //   * strided path (NCHW, C=3 frames, odd layouts): one thread per pixel,
 //     lanes along W (coalesced per channel plane), channel loop unrolled x4.
 // Source coordinates are computed once per pixel and reused for all channels.
+#include <cuda.h>     // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include <stdlib.h>
 
 #include "dvc_common.cuh"
@@ -50,6 +51,7 @@ struct WarpTask {
   int prefetch;      // vec4: 0 none, 1 south tap row if the flow is coherent (default), 2 both rows, 3 south always
   int tiles_x, tiles_y;
   int first_block, n_blocks;
+  int pl_tma;        // planar path: 1 = boxes staged by TMA (fixed 64-float pitch, unaligned origin)
 };
 struct WarpBatch {
   WarpTask t[kMaxTasks];
@@ -322,9 +324,17 @@ warp_multi_kernel(const __grid_constant__ WarpBatch batch) {
 #ifndef DVC_PLANAR_PX   // 3 / 4 pixels per thread (taller tiles): 3-5 % faster on gentle flows, 5-100 %
 #define DVC_PLANAR_PX 2 // slower on rough ones (fewer tiles fit their box) -- measured, 2 kept
 #endif
+#ifndef DVC_PLANAR_PITCH
+// Row pitch of the staged box in floats.  64 (= 0 mod 32 banks): a tap's bank is its COLUMN
+// mod 32 whatever row it sits in, so the 32 lanes of a warp -- adjacent pixels, hence (for a
+// coherent flow) adjacent tap columns spread over a few rows -- gather without bank conflicts.
+// 0 = round 1's variable odd-float4 pitch (56 % of the gather wavefronts were conflicts).
+#define DVC_PLANAR_PITCH 64
+#endif
 constexpr int kPlPx = DVC_PLANAR_PX;                  // pixels per thread
 constexpr int kPlTileW = DVC_PLANAR_VERT ? 32 : 32 * kPlPx, kPlTileH = DVC_PLANAR_VERT ? 8 * kPlPx : 8;
-constexpr int kPlBoxW4 = DVC_PLANAR_VERT ? 18 : 28, kPlBoxH = DVC_PLANAR_VERT ? 8 * kPlPx + 24 : 26;   // staged box limits
+constexpr int kPlBoxW4 = DVC_PLANAR_PITCH ? DVC_PLANAR_PITCH / 4 : (DVC_PLANAR_VERT ? 18 : 28);
+constexpr int kPlBoxH = DVC_PLANAR_VERT ? 8 * kPlPx + 24 : 26;   // staged box limits
 constexpr int kPlBufFloats = kPlBoxW4 * 4 * kPlBoxH;  // 2912 floats = 11648 B
 #ifndef DVC_PLANAR_BUFS
 #define DVC_PLANAR_BUFS 4
@@ -332,6 +342,99 @@ constexpr int kPlBufFloats = kPlBoxW4 * 4 * kPlBoxH;  // 2912 floats = 11648 B
 constexpr int kPlBufs = DVC_PLANAR_BUFS;              // channel planes in flight
 constexpr int kPlSlots = (kPlBoxW4 * kPlBoxH + kThreads - 1) / kThreads;  // float4 per thread, 3
 constexpr int kPlSmemBytes = kPlBufs * kPlBufFloats * 4;
+
+// Box of a tile's taps -> does it fit the staging buffers?  Evaluated identically by the
+// staged launch and by its complement (the gather launch), so no flag buffer is needed.
+struct PlBox {
+  int bx0, by0, hh, w4;   // origin, rows, width in float4 columns (cp.async variant)
+  bool fits;
+};
+__device__ __forceinline__ PlBox planar_box(int xmin, int xmax, int ymin, int ymax, int H, int W,
+                                            int tma) {
+  PlBox b;
+  const int bx1 = min(xmax + 1, W - 1), by1 = min(ymax + 1, H - 1);
+  b.by0 = ymin;
+  b.hh = by1 - ymin + 1;
+  if (tma) {                       // TMA: any origin, 64 columns
+    b.bx0 = xmin;
+    b.w4 = 16;
+    b.fits = (bx1 - xmin + 1) <= 64 && b.hh <= kPlBoxH;
+  } else {                         // cp.async: 16-byte aligned origin
+    b.bx0 = xmin & ~3;
+    b.w4 = (bx1 - b.bx0 + 4) >> 2;
+#if DVC_PLANAR_PITCH
+    b.fits = b.w4 <= kPlBoxW4 && b.hh <= kPlBoxH;
+#else
+    b.fits = (((b.w4 & 1) ? b.w4 : b.w4 + 1) <= kPlBoxW4) && b.hh <= kPlBoxH;
+#endif
+  }
+  return b;
+}
+
+// Per-thread state of the staged plane loop.  The loop is unrolled over the kPlBufs staging
+// buffers so that every shared-memory address is `register + immediate` and the copy / gather
+// of a plane cost a fixed, small instruction count (the first version re-derived tap indexes,
+// buffer bases and border predicates per plane: 107 SASS instructions per plane and thread,
+// 71 % of the issue slots; ncu, profiles/r02_planar.md).
+struct PlanarLoop {
+  const float* src[(kPlBoxW4 * kPlBoxH + kThreads - 1) / kThreads];
+  uint32_t dst[(kPlBoxW4 * kPlBoxH + kThreads - 1) / kThreads];
+  int i_nw[kPlPx], i_ne[kPlPx], i_sw[kPlPx], i_se[kPlPx];
+  float* pk[kPlPx];
+  Taps T[kPlPx];
+  bool valid[kPlPx];
+};
+
+template <bool kFast>
+__device__ __forceinline__ void planar_planes(PlanarLoop& L, float* __restrict__ smem, const int C,
+                                              const long long im_c, const long long out_c) {
+  constexpr int kSlots = (kPlBoxW4 * kPlBoxH + kThreads - 1) / kThreads;
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+  auto issue = [&](int c, int buf) {
+    if (c < C) {
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) {
+        if (L.dst[k] != 0xffffffffu)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                           s_base + L.dst[k] + (uint32_t)(buf * kPlBufFloats * 4)),
+                       "l"(L.src[k])
+                       : "memory");
+        L.src[k] += im_c;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // empty groups keep the count uniform
+  };
+#pragma unroll
+  for (int c = 0; c < kPlBufs - 1; ++c) issue(c, c);
+
+#pragma unroll 1
+  for (int c0 = 0; c0 < C; c0 += kPlBufs) {
+#pragma unroll
+    for (int u = 0; u < kPlBufs; ++u) {
+      const int c = c0 + u;
+      if (c < C) {                  // block-uniform
+        asm volatile("cp.async.wait_group %0;" ::"n"(kPlBufs - 2) : "memory");   // plane c has landed
+        __syncthreads();            // ... for every thread; and everyone is done with plane c - 1
+        issue(c + kPlBufs - 1, (u + kPlBufs - 1) % kPlBufs);   // into the buffer plane c - 1 used
+        const float* __restrict__ b = smem + u * kPlBufFloats;
+#pragma unroll
+        for (int k = 0; k < kPlPx; ++k) {
+          const float vnw = b[L.i_nw[k]];
+          float vne = b[L.i_ne[k]], vsw = b[L.i_sw[k]], vse = b[L.i_se[k]];
+          if (!kFast) {
+            const bool in_e = L.T[k].dx != 0, in_s = L.T[k].dy != 0;
+            vne = in_e ? vne : 0.f;
+            vsw = in_s ? vsw : 0.f;
+            vse = (in_e && in_s) ? vse : 0.f;
+          }
+          if (kFast || L.valid[k]) __stcs(L.pk[k], blend(vnw, vne, vsw, vse, L.T[k]));
+          L.pk[k] += out_c;
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // kStaged = true : tiles whose tap box fits are gathered from shared memory, others return;
 // kStaged = false: the complementary launch (no shared memory -> all of L1 for the
@@ -390,19 +493,19 @@ warp_planar_kernel(const __grid_constant__ WarpTask t) {
     ymin = min(ymin, s_red[16 + i]);
     ymax = max(ymax, s_red[24 + i]);
   }
-  const int bx0 = xmin & ~3;                       // 16-byte aligned column
-  const int bx1 = min(xmax + 1, W - 1), by0 = ymin, by1 = min(ymax + 1, H - 1);
-  const int hh = by1 - by0 + 1;
-  int w4 = (bx1 - bx0 + 4) >> 2;                   // box width in float4 columns
+  const PlBox box = planar_box(xmin, xmax, ymin, ymax, H, W, kStaged ? 0 : t.pl_tma);
+  const int bx0 = box.bx0, by0 = box.by0, hh = box.hh, w4 = box.w4;
+#if DVC_PLANAR_PITCH
+  constexpr int pitch = DVC_PLANAR_PITCH;      // rows are a fixed pitch apart
+#else
   // an odd float4 pitch spreads the rows of a box over the banks (pitch = 4 mod 8 words)
-  const int pitch4 = (w4 & 1) ? w4 : w4 + 1;
-  const int pitch = pitch4 * 4;
+  const int pitch = ((w4 & 1) ? w4 : w4 + 1) * 4;
+#endif
 
   const float* __restrict__ im_n = t.im + n * t.im_n;
   float* __restrict__ po = t.out + n * t.out_n;
 
-  const bool fits = pitch4 <= kPlBoxW4 && hh <= kPlBoxH;
-  if (fits != kStaged) return;
+  if (box.fits != kStaged) return;
   if (!kStaged) {
     // ---- incoherent flow: global gathers (warp_tile_strided's arithmetic), both
     // pixels of the thread interleaved so 8 independent loads are in flight per channel
@@ -440,58 +543,188 @@ warp_planar_kernel(const __grid_constant__ WarpTask t) {
   // ---- staged path ------------------------------------------------------------------
   // this thread's share of a box copy: the same (row, float4 column) slots for every
   // plane; the source pointers advance by one plane per use
-  const float* src[kPlSlots];
-  uint32_t dst_off[kPlSlots];
+  PlanarLoop L;
   const int n_vec = w4 * hh;
 #pragma unroll
   for (int k = 0; k < kPlSlots; ++k) {
     const int e = threadIdx.x + k * kThreads;
     const int r = e / w4, c4 = e - r * w4;
-    src[k] = im_n + (long long)(by0 + r) * t.im_h + bx0 + c4 * 4;
-    dst_off[k] = e < n_vec ? (uint32_t)(r * pitch + c4 * 4) * 4u : 0xffffffffu;
+    L.src[k] = im_n + (long long)(by0 + r) * t.im_h + bx0 + c4 * 4;
+    L.dst[k] = e < n_vec ? (uint32_t)(r * pitch + c4 * 4) * 4u : 0xffffffffu;
   }
-  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(pl_smem);
-  int issued = 0;   // planes issued so far (also selects the buffer)
-  auto issue = [&]() {
-    if (issued < t.C) {
-      const uint32_t buf = s_base + (uint32_t)((issued % kPlBufs) * kPlBufFloats) * 4u;
-#pragma unroll
-      for (int k = 0; k < kPlSlots; ++k) {
-        if (dst_off[k] != 0xffffffffu)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf + dst_off[k]),
-                       "l"(src[k])
-                       : "memory");
-        src[k] += t.im_c;
-      }
-    }
-    ++issued;
-    asm volatile("cp.async.commit_group;" ::: "memory");   // empty groups keep the count uniform
-  };
-#pragma unroll
-  for (int c = 0; c < kPlBufs - 1; ++c) issue();
-
-  int i_nw[kPlPx], i_ne[kPlPx], i_sw[kPlPx], i_se[kPlPx];
-  float* pk[kPlPx];
+  bool all_valid = true;
 #pragma unroll
   for (int k = 0; k < kPlPx; ++k) {
     const bool in_e = T[k].dx != 0, in_s = T[k].dy != 0;
-    i_nw[k] = (T[k].y0 - by0) * pitch + (T[k].x0 - bx0);
+    L.i_nw[k] = (T[k].y0 - by0) * pitch + (T[k].x0 - bx0);
+    L.i_ne[k] = L.i_nw[k] + (in_e ? 1 : 0);
+    L.i_sw[k] = L.i_nw[k] + (in_s ? pitch : 0);
+    L.i_se[k] = L.i_sw[k] + (in_e ? 1 : 0);
+    L.pk[k] = po + hcl[k] * t.out_h + wcl[k] * t.out_w;
+    L.T[k] = T[k];
+    L.valid[k] = valid[k];
+    all_valid = all_valid && valid[k];
+  }
+  // Block-uniform fast case: the whole tile is inside the image and no tap of it touches the
+  // east / south border, so neither the out-of-image masks nor the store predicate is needed.
+  const bool fast = (xmax + 1 <= W - 1) && (ymax + 1 <= H - 1) && (tx + 1) * kPlTileW <= W &&
+                    (ty + 1) * kPlTileH <= H;
+  if (fast)
+    planar_planes<true>(L, pl_smem, t.C, t.im_c, t.out_c);
+  else
+    planar_planes<false>(L, pl_smem, t.C, t.im_c, t.out_c);
+}
+
+// ---------------------------------------------------------------------------
+// planar path, boxes staged by TMA (cp.async.bulk.tensor.4d)
+//
+// The cp.async variant above spends a quarter of its instructions, and -- at
+// 8 LSU cycles per LDGSTS warp-instruction -- most of the SM's load/store pipe on
+// copying the box (ncu: L1/shared pipe 78 %, issue slots 67 %).  A tap box is a
+// rectangle of one channel plane: exactly one TMA tile.  One elected thread
+// issues ONE instruction per plane; the copy engine writes the 64 x BH box into
+// shared memory with a dense 64-float pitch (bank = column mod 32: the gather of a
+// coherent flow is conflict-free, see DVC_PLANAR_PITCH) and signals an mbarrier.
+// Three tensor maps (box heights 24 / 32 / 40 rows) keep the over-fetch down; the
+// box origin needs no alignment, out-of-image parts are zero-filled and never
+// read (out-of-image taps are masked, as everywhere).
+// ---------------------------------------------------------------------------
+constexpr int kTmaBoxW = 64;
+constexpr int kTmaH0 = 24, kTmaH1 = 32, kTmaH2 = kPlBoxH;     // box heights of the three maps
+constexpr int kTmaBufBytes = kTmaBoxW * kPlBoxH * 4;          // 10 240
+constexpr int kTmaSmemBytes = kPlBufs * kTmaBufBytes + 128;   // + alignment slack
+struct alignas(64) PlanarMaps {
+  CUtensorMap m[3];
+};
+
+__device__ __forceinline__ uint32_t pl_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pl_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 20)) __trap();   // a lost copy traps instead of hanging the device
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, DVC_PLANAR_MINB)
+warp_planar_tma_kernel(const __grid_constant__ WarpTask t, const __grid_constant__ PlanarMaps maps) {
+  extern __shared__ __align__(128) unsigned char pl_tma_smem[];
+  __shared__ int s_red[32];
+  __shared__ __align__(8) unsigned long long s_full[kPlBufs];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile = blockIdx.x;
+  const int tx = tile % t.tiles_x;
+  const int rest = tile / t.tiles_x;
+  const int ty = rest % t.tiles_y;
+  const int n = rest / t.tiles_y;
+  const int H = t.g.H, W = t.g.W;
+  const float* __restrict__ fl = t.flow + n * t.fl_n;
+
+  Taps T[kPlPx];
+  bool valid[kPlPx];
+  int wcl[kPlPx], hcl[kPlPx];
+  int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+#pragma unroll
+  for (int k = 0; k < kPlPx; ++k) {
+    const int w = tx * kPlTileW + (DVC_PLANAR_VERT ? 0 : k * 32) + lane;
+    const int h = ty * kPlTileH + wid + (DVC_PLANAR_VERT ? k * 8 : 0);
+    valid[k] = (w < W) && (h < H);
+    wcl[k] = min(w, W - 1);
+    hcl[k] = min(h, H - 1);
+    const float fx = fetch_flow(fl, t.fl_h, t.fl_w, hcl[k], wcl[k], t.flow_level);
+    const float fy = fetch_flow(fl + t.fl_c, t.fl_h, t.fl_w, hcl[k], wcl[k], t.flow_level);
+    T[k] = make_taps(t.g, hcl[k], wcl[k], fx, fy);
+    xmin = min(xmin, T[k].x0); xmax = max(xmax, T[k].x0);
+    ymin = min(ymin, T[k].y0); ymax = max(ymax, T[k].y0);
+  }
+  xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+  ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+  if (lane == 0) {
+    s_red[wid] = xmin;
+    s_red[8 + wid] = xmax;
+    s_red[16 + wid] = ymin;
+    s_red[24 + wid] = ymax;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int b = 0; b < kPlBufs; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pl_smem_u32(&s_full[b])), "r"(1)
+                   : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    xmin = min(xmin, s_red[i]);
+    xmax = max(xmax, s_red[8 + i]);
+    ymin = min(ymin, s_red[16 + i]);
+    ymax = max(ymax, s_red[24 + i]);
+  }
+  const PlBox box = planar_box(xmin, xmax, ymin, ymax, H, W, 1);
+  if (!box.fits) return;           // block-uniform: the gather launch takes this tile
+  const int bx0 = box.bx0, by0 = box.by0;
+  const int sel = box.hh <= kTmaH0 ? 0 : (box.hh <= kTmaH1 ? 1 : 2);
+  const uint32_t bytes = (uint32_t)(kTmaBoxW * 4) *
+                         (uint32_t)(sel == 0 ? kTmaH0 : (sel == 1 ? kTmaH1 : kTmaH2));
+  const CUtensorMap* map = &maps.m[sel];
+
+  // 128-byte aligned staging buffers
+  const uint32_t s_base = (pl_smem_u32(pl_tma_smem) + 127u) & ~127u;
+  const float* __restrict__ sbuf0 = reinterpret_cast<const float*>(
+      pl_tma_smem + (s_base - pl_smem_u32(pl_tma_smem)));
+  const int C = t.C;
+  auto issue = [&](int c) {        // thread 0 only
+    if (c < C) {
+      const int b = c % kPlBufs;
+      const uint32_t bar = pl_smem_u32(&s_full[b]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+          "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+          ::"r"(s_base + (uint32_t)(b * kTmaBufBytes)), "l"(map), "r"(bx0), "r"(by0), "r"(c), "r"(n),
+            "r"(bar)
+          : "memory");
+    }
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < kPlBufs - 1; ++c) issue(c);
+  }
+
+  int i_nw[kPlPx], i_ne[kPlPx], i_sw[kPlPx], i_se[kPlPx];
+  float* pk[kPlPx];
+  float* __restrict__ po = t.out + n * t.out_n;
+#pragma unroll
+  for (int k = 0; k < kPlPx; ++k) {
+    const bool in_e = T[k].dx != 0, in_s = T[k].dy != 0;
+    i_nw[k] = (T[k].y0 - by0) * kTmaBoxW + (T[k].x0 - bx0);
     i_ne[k] = i_nw[k] + (in_e ? 1 : 0);
-    i_sw[k] = i_nw[k] + (in_s ? pitch : 0);
+    i_sw[k] = i_nw[k] + (in_s ? kTmaBoxW : 0);
     i_se[k] = i_sw[k] + (in_e ? 1 : 0);
     pk[k] = po + hcl[k] * t.out_h + wcl[k] * t.out_w;
   }
 #pragma unroll 1
-  for (int c = 0; c < t.C; ++c) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(kPlBufs - 2) : "memory");   // plane c has landed
-    __syncthreads();            // ... for every thread; and everyone is done with plane c - 1
-    issue();                    // into the buffer plane c - 1 used
-    const float* __restrict__ b = pl_smem + (c % kPlBufs) * kPlBufFloats;
+  for (int c = 0; c < C; ++c) {
+    __syncthreads();               // everyone is done with plane c - 1: its buffer is free
+    if (threadIdx.x == 0) issue(c + kPlBufs - 1);
+    const int b = c % kPlBufs;
+    pl_mbar_wait(pl_smem_u32(&s_full[b]), (uint32_t)((c / kPlBufs) & 1));
+    const float* __restrict__ sb = sbuf0 + b * (kTmaBufBytes / 4);
 #pragma unroll
     for (int k = 0; k < kPlPx; ++k) {
       const bool in_e = T[k].dx != 0, in_s = T[k].dy != 0;
-      const float vnw = b[i_nw[k]];
-      float vne = b[i_ne[k]], vsw = b[i_sw[k]], vse = b[i_se[k]];
+      const float vnw = sb[i_nw[k]];
+      float vne = sb[i_ne[k]], vsw = sb[i_sw[k]], vse = sb[i_se[k]];
       vne = in_e ? vne : 0.f;
       vsw = in_s ? vsw : 0.f;
       vse = (in_e && in_s) ? vse : 0.f;
@@ -499,7 +732,60 @@ warp_planar_kernel(const __grid_constant__ WarpTask t) {
       pk[k] += t.out_c;
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// OFF by default and UNVERIFIED: on this pool's B200 boxes every cp.async.bulk.tensor
+// (UTMALDG) raises cudaErrorIllegalInstruction -- our own minimal program with descriptors in
+// param or global memory, ranks 2-4, with and without swizzle, and Triton's stock
+// tensor-descriptor kernel alike (tools/tma_probe.cu, tools/triton_tma_probe.py,
+// profiles/r02_tma_probe.md) -- so this path could not be run.  DVC_WARP_PLANAR_TMA=1 enables it.
+static int planar_tma_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVC_WARP_PLANAR_TMA");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+// tensor maps over im[N][C][H][W] (element strides im_n, im_c, im_h, 1); false if not encodable
+static bool build_planar_maps(PlanarMaps& maps, const WarpTask& t, const dvc_warp_task& in) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || in.W < kTmaBoxW || in.H < 8) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.C, (cuuint64_t)in.N};
+  const cuuint64_t strides[3] = {(cuuint64_t)t.im_h * 4, (cuuint64_t)t.im_c * 4,
+                                 (cuuint64_t)t.im_n * 4};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0 || (strides[i] & 15) || strides[i] >= (1ULL << 40)) return false;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const int heights[3] = {kTmaH0, kTmaH1, kTmaH2};
+  for (int i = 0; i < 3; ++i) {
+    const cuuint32_t box[4] = {(cuuint32_t)kTmaBoxW, (cuuint32_t)heights[i], 1, 1};
+    CUresult r = enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in.im), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  return true;
 }
 
 static int planar_min_c() {   // tuning knob (not API)
@@ -528,8 +814,24 @@ static int launch_planar(WarpTask t, const dvc_warp_task& in, cudaStream_t strea
     if (e != cudaSuccess)
       return fail(DVC_ERR_CUDA, "flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  warp_planar_kernel<true><<<(unsigned)nb, kThreads, kPlSmemBytes, stream>>>(t);
-  int rc = check_launch("warp_planar_kernel<staged>");
+  int rc;
+  PlanarMaps maps;
+  t.pl_tma = (planar_tma_mode() && build_planar_maps(maps, t, in)) ? 1 : 0;
+  if (t.pl_tma) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(warp_planar_tma_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+      if (e != cudaSuccess)
+        return fail(DVC_ERR_CUDA, "flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    warp_planar_tma_kernel<<<(unsigned)nb, kThreads, kTmaSmemBytes, stream>>>(t, maps);
+    rc = check_launch("warp_planar_tma_kernel");
+  } else {
+    warp_planar_kernel<true><<<(unsigned)nb, kThreads, kPlSmemBytes, stream>>>(t);
+    rc = check_launch("warp_planar_kernel<staged>");
+  }
   if (rc) return rc;
   warp_planar_kernel<false><<<(unsigned)nb, kThreads, 0, stream>>>(t);
   return check_launch("warp_planar_kernel<gather>");

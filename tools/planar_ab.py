@@ -33,12 +33,21 @@ with torch.no_grad():
 print(json.dumps(res))
 ''' % ROOT
 out = {}
-import itertools
-for planar, lib in (("1", None), ("0", None)):
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DVC_WARP_PLANAR=planar, **({"DVC_B200_LIB": os.path.join(ROOT, "deepvideocodec_b200", lib)} if lib else {})), capture_output=True, text=True)
+# usage: planar_ab.py [libA.so libB.so ...]  (A/B builds next to libdvc_b200.so); default: shipped
+# library, planar vs strided
+# an argument may carry environment settings: libX.so:VAR=1:VAR2=0
+variants = [("1", a) for a in sys.argv[1:]] or [("1", None), ("0", None)]
+for planar, spec in variants:
+    lib, extra = None, {}
+    if spec:
+        parts = spec.split(":")
+        lib = parts[0] or None
+        extra = dict(kv.split("=", 1) for kv in parts[1:])
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DVC_WARP_PLANAR=planar, **extra, **({"DVC_B200_LIB": os.path.join(ROOT, "deepvideocodec_b200", lib)} if lib else {})), capture_output=True, text=True)
+    key = ("planar" if planar == "1" else "strided") + (spec or "")
     try:
-        out[("planar" if planar == "1" else "strided") + (lib or "")] = json.loads(r.stdout.strip().splitlines()[-1])
+        out[key] = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception:
-        out[("planar" if planar == "1" else "strided") + (lib or "")] = r.stderr[-800:]
+        out[key] = r.stderr[-800:]
 print(json.dumps(out, indent=1))
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "planar_ab.json"), "w"), indent=1)

@@ -89,8 +89,11 @@ def main():
         aux_opt.zero_grad(set_to_none=True)
         torch.manual_seed(seed)                               # training noise: same in both arms
         kw = {"motion_pretrain": stage == "motion", "frame_pretrain": stage == "frame"}
-        out = ddp(list(fr), **kw)
-        oc = crit(out, fr[1:])
+        # motion pre-training returns no dpb context (video_model.py:565-566), so the reference
+        # itself can only run it on 2-frame samples (:543-549 would raise KeyError)
+        seq = fr[:2] if stage == "motion" else fr
+        out = ddp(list(seq), **kw)
+        oc = crit(out, seq[1:])
         oc["loss"].backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)      # train.py:332-333
         opt.step()
