@@ -23,35 +23,49 @@ import torch
 
 from . import _native as nat
 
-__all__ = ["DEFAULT_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "auto_stream_symbols", "build_indexes", "collect",
+__all__ = ["DEFAULT_STREAM_SYMBOLS", "PINNED_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "auto_stream_symbols", "build_indexes", "collect",
            "decode_stage_a", "decode_stage_b", "pmf_to_quantized_cdf", "quantize_symbols",
            "rans_decode", "rans_encode", "rans_encode_async", "stream_symbols_of"]
 
 MAGIC = 0x31435644                     # "DVC1"
-DEFAULT_STREAM_SYMBOLS = int(os.environ.get("DVC_RANS_STREAM_SYMBOLS", "4096"))
-MIN_STREAMS = int(os.environ.get("DVC_RANS_MIN_STREAMS", "0"))   # 0: policy below is off
+_ENV_S = os.environ.get("DVC_RANS_STREAM_SYMBOLS")
+# Sub-stream length when nothing is known about the payload (module-level compress()):
+DEFAULT_STREAM_SYMBOLS = int(_ENV_S) if _ENV_S is not None else 4096
+# A pinned length overrides the payload-driven policy (DVC_RANS_STREAM_SYMBOLS; 0 = raw stock stream)
+PINNED_STREAM_SYMBOLS = int(_ENV_S) if _ENV_S is not None else None
+MIN_STREAMS = int(os.environ.get("DVC_RANS_MIN_STREAMS", "8"))
 MIN_STREAM_SYMBOLS = 256
+STREAM_OVERHEAD_BYTES = 12             # per sub-stream: 4 B length word + 8 B rans64 flush
+OVERHEAD_TARGET = float(os.environ.get("DVC_RANS_OVERHEAD", "0.01"))
 
 
-def auto_stream_symbols(n_symbols):
+def auto_stream_symbols(n_symbols, est_bytes=None):
     """Sub-stream length used when the caller does not choose one.
 
-    Range coding is serial inside a sub-stream (~0.1 us per symbol), so a launch
-    lasts ``stream_symbols`` x that no matter how few symbols there are.  With
-    ``DVC_RANS_MIN_STREAMS = k > 0`` a short tensor (the hyper-latent z: 32 640
-    symbols at 1080p) is cut into at least k pieces of a power-of-two length:
-    k = 64 makes a 1080p frame's encode 2.5x and decode 1.8x shorter, but costs
-    ~12 bytes per piece -- +0.3 % bytes at 7 bits/symbol, +4 % at 0.5 bits/symbol
-    (profiles/r01_coder_bench.json, "auto").  Bytes matter more than a
-    millisecond to a codec, so the default is off; the z coder is overlapped with
-    the convolutions that follow it instead (``overlap=True``).  The length is
+    Range coding is serial inside a sub-stream, so a launch lasts
+    ``stream_symbols`` x the per-symbol chain latency no matter how few symbols
+    there are -- more sub-streams are faster -- but each sub-stream costs
+    ``STREAM_OVERHEAD_BYTES`` = 12 bytes.  A fixed length of 4 096 symbols is
+    +0.3 % bytes at 7 bits/symbol but +15 ... 80 % at the 0.03 - 0.15
+    bits/symbol of a low-rate P-frame, so the policy is driven by the
+    PAYLOAD: with an estimate of the coded size (the fused ``sum ln p`` of the
+    likelihood kernel, free in the fused context models) the number of
+    sub-streams is the largest that keeps the container overhead at
+    ``DVC_RANS_OVERHEAD`` (1 %) of the payload, but at least
+    ``DVC_RANS_MIN_STREAMS`` (8; 96 bytes) so that a near-empty tensor does not
+    decode as one serial chain.  Without an estimate the length is
+    ``DEFAULT_STREAM_SYMBOLS``; ``DVC_RANS_STREAM_SYMBOLS`` pins it (0 = one raw
+    stock stream, byte-compatible with CompressAI, for interop).  The length is
     recorded in the container header, so decoders need no matching policy."""
-    s = DEFAULT_STREAM_SYMBOLS
-    if s <= 0 or MIN_STREAMS <= 0:
-        return s
-    while s > MIN_STREAM_SYMBOLS and n_symbols < MIN_STREAMS * s:
-        s //= 2
-    return s
+    if PINNED_STREAM_SYMBOLS is not None:
+        return PINNED_STREAM_SYMBOLS
+    if est_bytes is None or DEFAULT_STREAM_SYMBOLS <= 0:
+        return DEFAULT_STREAM_SYMBOLS
+    n = int(OVERHEAD_TARGET * float(est_bytes) // STREAM_OVERHEAD_BYTES)
+    n = max(n, MIN_STREAMS, 1)
+    n = min(n, max(1, (n_symbols + MIN_STREAM_SYMBOLS - 1) // MIN_STREAM_SYMBOLS))
+    s = (n_symbols + n - 1) // n
+    return max(MIN_STREAM_SYMBOLS, (s + 255) // 256 * 256)     # whole staging chunks
 
 
 _side_streams = {}
@@ -171,15 +185,10 @@ def _index_args(indexes, scales, scale_table, shape, device):
     return None, None, None, 0, None, keep        # channel index (entropy bottleneck)
 
 
-_status = {}
-
-
 def _status_word(device):
-    t = _status.get(device.index)
-    if t is None:
-        t = torch.zeros(1, dtype=torch.int32, device=device)
-        _status[device.index] = t
-    return t
+    """One status word per launch: a failed or abandoned encode cannot leave a
+    flag behind that an unrelated later decode would trip over."""
+    return torch.zeros(1, dtype=torch.int32, device=device)
 
 
 class PendingStreams:
@@ -194,13 +203,17 @@ class PendingStreams:
 
 
 def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, scales=None,
-                      scale_table=None, scale_bound=0.11, stream_symbols=None, overlap=False):
+                      scale_table=None, scale_bound=0.11, stream_symbols=None, overlap=False,
+                      est_bytes=None):
     """Launch the encoder for one tensor ``[N,C,H,W]``; no host synchronisation.
 
     Symbols: ``symbols`` (int32) or ``round(x - means)``.  Table indexes:
     ``indexes`` (int), or derived from ``scales`` like ``build_indexes``, or --
     neither -- the channel number.  ``collect`` turns pending results into
     ``bytes`` with a single device->host round trip for any number of them.
+
+    ``est_bytes``: estimated coded size of ONE sample (``-sum log2 p / 8``), used by
+    ``auto_stream_symbols`` to bound the container overhead.
 
     ``overlap=True`` runs the encoder on a per-device side stream (ordered after
     everything already queued on the current stream): the coder keeps a handful
@@ -225,7 +238,7 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
     ip, sp, tp, T, sst, keep = _index_args(indexes, scales, scale_table, src.shape, dev)
     L = c * h * w
     if stream_symbols is None:
-        stream_symbols = auto_stream_symbols(L)
+        stream_symbols = auto_stream_symbols(L, est_bytes)   # est_bytes: per sample
     lib = nat.lib()
     cap = lib.dvc_rans_max_bytes(L, int(stream_symbols))
     scratch_bytes = lib.dvc_rans_scratch_bytes(n, L, int(stream_symbols))
@@ -251,8 +264,13 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
         if overlap:
             done = torch.cuda.Event()
             done.record(side)
+            # these blocks belong to the current stream's allocator pool: tell it the side
+            # stream uses them, so dropping the pending object before collect() (an exception
+            # between the head and the tail of a compress call) cannot hand them out early
+            for t in [out, out_bytes, scratch, status, x, means, symbols] + list(keep):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(side)
     nat.check(rc, "dvc_rans_encode")
-    # every tensor the side stream touches stays referenced until collect() has joined it
     return PendingStreams(out, out_bytes, status, cap, keep + [x, means, symbols, scratch], done)
 
 
@@ -264,10 +282,9 @@ def collect(pendings):
     for p in pendings:
         if p.done is not None:
             torch.cuda.current_stream(p.out.device).wait_event(p.done)
-    status = pendings[0].status
-    sizes = torch.cat([p.out_bytes for p in pendings] + [status.to(torch.int64)]).cpu().tolist()
-    if sizes[-1] != 0:
-        status.zero_()
+    sizes = torch.cat([p.out_bytes for p in pendings] +
+                      [p.status.to(torch.int64) for p in pendings]).cpu().tolist()
+    if any(sizes[-len(pendings):]):
         raise ValueError("compress: an index lies outside the CDF tables")
     pieces, k = [], 0
     for p in pendings:
@@ -351,7 +368,6 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
     nat.check(rc, "dvc_rans_decode")
     st = int(status.item())
     if st != 0:
-        status.zero_()
         raise ValueError("decompress: " + ("an index lies outside the CDF tables" if st == 1
                                            else "malformed bit-stream container"))
     return out_s if want_symbols else out_f
@@ -366,7 +382,13 @@ def decode_stage_a(q0, means, scales):
     n, c, h, w = means.shape
     if q0.dtype != torch.int32 or tuple(q0.shape) != (n, c // 2, h, w) or not q0.is_contiguous():
         raise nat.DvcError("decode_stage_a: q0 must be contiguous int32 [N, C/2, H, W]")
-    params = torch.empty((n, 3 * c, h, w), dtype=torch.float32, device=means.device)
+    # same memory-format rule as the encoder's stage A (context._stage_a_fwd), keyed on the
+    # prior means both sides compute identically: y_spatial_prior must see the same layout in
+    # the encoder and the decoder, or cuDNN may pick different algorithms and a 1-ulp
+    # difference in its output can move a scale across a table threshold (decoder desync)
+    cl = means.is_contiguous(memory_format=torch.channels_last) and not means.is_contiguous()
+    params = torch.empty((n, 3 * c, h, w), dtype=torch.float32, device=means.device,
+                         memory_format=torch.channels_last if cl else torch.contiguous_format)
     with nat.device_of(means):
         rc = nat.lib().dvc_dual_prior_decode_stage_a(
             q0.data_ptr(), means.data_ptr(), scales.data_ptr(), params.data_ptr(), n, c, h, w,

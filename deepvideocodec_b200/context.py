@@ -17,6 +17,8 @@ reference's context-model instance) so ``deepvideocodec_b200.patch`` can bind
 them onto the stock classes; signatures and return structures are the
 reference's.
 """
+import math
+
 import torch
 
 from . import _native as nat
@@ -45,7 +47,9 @@ def _check_latents(y, means, scales, who):
 # ---------------------------------------------------------------------------
 def _stage_a_fwd(y, means, scales):
     n, c, h, w = y.shape
-    cl = y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()
+    # keyed on the prior means (not on y): the decoder has no y, and both sides must hand
+    # y_spatial_prior the same memory format (coder.decode_stage_a)
+    cl = means.is_contiguous(memory_format=torch.channels_last) and not means.is_contiguous()
     params = torch.empty((n, 3 * c, h, w), dtype=y.dtype, device=y.device,
                          memory_format=torch.channels_last if cl else torch.contiguous_format)
     with nat.device_of(y):
@@ -129,18 +133,21 @@ class _StageBGcFn(torch.autograd.Function):
 def _gc_bounds(gc):
     """(scale_bound, likelihood_bound) of a GaussianConditional -- ours or the
     real CompressAI module (reads the buffers once and caches the floats)."""
-    cached = getattr(gc, "_dvc_bounds", None)
-    if cached is not None:
-        return cached
     sb_mod = gc.lower_bound_scale
-    sb = sb_mod.value() if hasattr(sb_mod, "value") else float(sb_mod.bound.detach().cpu().reshape(-1)[0])
-    if getattr(gc, "use_likelihood_bound", True):
-        lb_mod = gc.likelihood_lower_bound
-        lb = lb_mod.value() if hasattr(lb_mod, "value") else float(lb_mod.bound.detach().cpu().reshape(-1)[0])
-    else:
-        lb = float("-inf")
-    gc._dvc_bounds = (sb, lb)
-    return gc._dvc_bounds
+    lb_mod = gc.likelihood_lower_bound if getattr(gc, "use_likelihood_bound", True) else None
+    if hasattr(sb_mod, "value") and (lb_mod is None or hasattr(lb_mod, "value")):
+        # our own holders keep a host float that load_state_dict refreshes: nothing to cache
+        return sb_mod.value(), (lb_mod.value() if lb_mod is not None else float("-inf"))
+    # foreign (real CompressAI) modules: one device read, cached until a bound buffer changes
+    bufs = [sb_mod.bound] + ([lb_mod.bound] if lb_mod is not None else [])
+    key = tuple((b.data_ptr(), b._version) for b in bufs)
+    cached = getattr(gc, "_dvc_bounds", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    sb = float(sb_mod.bound.detach().cpu().reshape(-1)[0])
+    lb = float(lb_mod.bound.detach().cpu().reshape(-1)[0]) if lb_mod is not None else float("-inf")
+    gc._dvc_bounds = (key, (sb, lb))
+    return sb, lb
 
 
 def dual_prior_stage_b_gc(y, means, scales, prior, gc, training, want_params=False,
@@ -251,9 +258,13 @@ def _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending):
     gc = self.gaussian_conditional
     params = dual_prior_stage_a(y, means_hat, scales_hat)
     prior = self.y_spatial_prior(params)
-    y_hat, _, _, _, planes = dual_prior_stage_b_gc(
+    y_hat, _, _, lik, planes = dual_prior_stage_b_gc(
         y, means_hat, scales_hat, prior, gc, training=False, compress=True)
     q_w0, q_w1, s_w0, s_w1 = planes
+    # estimated payload of one (sample, checkerboard pass): the likelihood kernel's fused
+    # sum(ln p) -- one 8-byte read -- sizes the sub-streams so that the container overhead
+    # stays at ~1 % of the bytes written (coder.auto_stream_symbols)
+    est_bytes = float(-lik._dvc_logsum.sum().item()) / (math.log(2.0) * 8.0 * 2.0 * y.size(0))
     tables = _coder_tables(gc)
     sb, _ = _gc_bounds(gc)
     n, ch, h, w = q_w0.shape
@@ -261,7 +272,8 @@ def _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending):
     # [2, N, C/2, H, W] buffer, coded here as a batch of 2N samples
     q_both, s_both = stacked_planes(planes)
     pending = coder.rans_encode_async(tables, x=q_both, scales=s_both,
-                                      scale_table=gc.scale_table, scale_bound=sb)
+                                      scale_table=gc.scale_table, scale_bound=sb,
+                                      est_bytes=est_bytes)
     y_strings, z_strings = coder.collect([pending, z_pending])
     return y_hat, {"strings": [y_strings[:n], y_strings[n:], z_strings],
                    "shape": z.size()[-2:]}

@@ -373,10 +373,12 @@ def eb_forward(eb, z, training=None, want_outputs=True, want_zhat=False):
     elif hasattr(bound, "value"):
         lb = bound.value()
     else:                                   # real CompressAI LowerBound module
-        lb = getattr(eb, "_dvc_lik_bound", None)
-        if lb is None:
-            lb = float(bound.bound.detach().cpu().reshape(-1)[0])
-            eb._dvc_lik_bound = lb
+        key = (bound.bound.data_ptr(), bound.bound._version)
+        cached = getattr(eb, "_dvc_lik_bound", None)
+        if cached is None or cached[0] != key:
+            cached = (key, float(bound.bound.detach().cpu().reshape(-1)[0]))
+            eb._dvc_lik_bound = cached
+        lb = cached[1]
     noise = None
     if training:
         # CompressAI draws the noise on its permuted [C, 1, N*H*W] view; drawing it
@@ -385,7 +387,9 @@ def eb_forward(eb, z, training=None, want_outputs=True, want_zhat=False):
         n_, c_, h_, w_ = z.shape
         noise = torch.empty((c_, n_, h_, w_), dtype=z.dtype, device=z.device).uniform_(
             -0.5, 0.5).permute(1, 0, 2, 3)
-    params = [getattr(eb, f"_matrix{k}") for k in range(5)] + [eb.quantiles]
+    params = [getattr(eb, f"_matrix{k}") for k in range(5)] + \
+             [getattr(eb, f"_bias{k}") for k in range(5)] + \
+             [getattr(eb, f"_factor{k}") for k in range(4)] + [eb.quantiles]
     needs_grad = torch.is_grad_enabled() and (
         z.requires_grad or any(p.requires_grad for p in params))
     if needs_grad:

@@ -345,14 +345,52 @@ class _Ctx(torch.nn.Module):
         self.entropy_bottleneck = eb
 
 
+def test_payload_driven_substreams(cuda_dev, gc_pair):
+    """at the 0.03 - 0.15 bits/symbol of a low-rate P-frame a fixed 4 096-symbol
+    partition costs +15 ... 80 % bytes.  The default partition is sized from the estimated
+    payload: container overhead <= 1 % of the bytes (+ the 8-stream floor, 96 B), at every rate;
+    and the bytes still decode to the symbols."""
+    import math
+    from deepvideocodec_b200 import coder
+    _, p = gc_pair
+    tables = p._tables()
+    g = torch.Generator().manual_seed(77)
+    shape = (1, 48, 68, 120)                                  # one checkerboard pass, frame model
+    L = shape[1] * shape[2] * shape[3]
+    for lo, hi, label in ((0.16, 0.2, "low"), (0.5, 1.0, "mid"), (4.0, 32.0, "high")):
+        scales = (torch.empty(shape).uniform_(lo, hi, generator=g)).to(cuda_dev)
+        x = torch.round(torch.randn(shape, generator=g).to(cuda_dev) * scales)
+        kw = dict(x=x, scales=scales, scale_table=p.scale_table, scale_bound=0.11)
+        raw = coder.rans_encode(tables, stream_symbols=0, **kw)[0]         # one stock stream
+        fixed = coder.rans_encode(tables, stream_symbols=4096, **kw)[0]
+        est = len(raw)                                        # what the likelihood sum predicts
+        auto = coder.rans_encode(tables, est_bytes=est, **kw)[0]
+        S = coder.stream_symbols_of(auto, L)
+        n_streams = (L + S - 1) // S
+        assert S == coder.auto_stream_symbols(L, est) and S % 256 == 0
+        overhead = len(auto) - len(raw)
+        assert overhead <= 0.0125 * len(raw) + coder.MIN_STREAMS * 16 + 32, (label, overhead, len(raw))
+        if label == "low":
+            assert len(raw) * 8 / L < 0.2                     # the regime the advice is about
+            assert len(fixed) - len(raw) > 5 * overhead       # what the fixed partition cost
+            assert n_streams == coder.MIN_STREAMS
+        if label == "high":
+            assert n_streams > (L + 4095) // 4096             # more parallel than the old default
+        out = coder.rans_decode([auto], tables, shape, scales=scales, scale_table=p.scale_table,
+                                scale_bound=0.11, device=cuda_dev)
+        assert torch.equal(out, x)
+    assert coder.auto_stream_symbols(L, None) == coder.DEFAULT_STREAM_SYMBOLS
+    assert math.isfinite(est)
+
+
 @pytest.mark.parametrize("frame", [False, True])
-@pytest.mark.parametrize("S", [0, 256])
+@pytest.mark.parametrize("S", [0, 256, None])
 def test_context_model_compress_decompress(cuda_dev, gc_pair, frame, S, monkeypatch):
     import deepvideocodec_b200 as dvc
     from deepvideocodec_b200 import coder
     from oracle import dmc_ref
     from oracle.compressai import entropy_models as oem
-    monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", S)
+    monkeypatch.setattr(coder, "PINNED_STREAM_SYMBOLS", S)
     o_gc, p_gc = gc_pair
     torch.manual_seed(31)
     o_eb = oem.EntropyBottleneck(6)

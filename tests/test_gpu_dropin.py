@@ -150,12 +150,12 @@ def test_encode_decode_inter_round_trip(cuda_dev, hw):
         x_dec, new_dpb = patched.decode_inter(enc_p["strings"], enc_p["shape"], dpb)
         assert (x_dec - x_fwd).abs().max().item() <= 1e-5
         assert set(new_dpb) == {"x_ref", "feature_ref", "y_ref", "y_mv_ref"}
-        saved = coder.DEFAULT_STREAM_SYMBOLS
-        coder.DEFAULT_STREAM_SYMBOLS = 0          # one raw stock rans64 stream per sample
+        saved = coder.PINNED_STREAM_SYMBOLS
+        coder.PINNED_STREAM_SYMBOLS = 0           # one raw stock rans64 stream per sample
         try:
             enc_raw = patched.encode_inter(f1, dpb)
         finally:
-            coder.DEFAULT_STREAM_SYMBOLS = saved
+            coder.PINNED_STREAM_SYMBOLS = saved
         if hw == (256, 256):                      # the CPU coder is slow: small size only
             enc_s = stock.encode_inter(f1, dpb)
             for key in ("motion", "frame"):
