@@ -6,7 +6,8 @@ behind the reference's own Python names.
 Importing the package never needs a GPU; calling an op needs the built
 ``libdvc_b200.so`` and CUDA fp32 tensors -- there is no fallback path.
 """
-from ._native import DvcError, LIB_PATH, build_library, declared_symbols, lib  # noqa: F401
+from ._native import (DvcError, LIB_PATH, build_library, built_hash, declared_symbols,  # noqa: F401
+                      lib, source_hash)
 from .context import (dual_prior_stage_a, dual_prior_stage_b_gc, forward_dual_prior,  # noqa: F401
                       frame_context_compress, frame_context_decompress,
                       frame_context_forward, motion_context_compress,

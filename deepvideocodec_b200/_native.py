@@ -30,23 +30,54 @@ class DvcError(RuntimeError):
     pass
 
 
-def nvcc_command(out_path=LIB_PATH, extra=()):
+_NVCC_FLAGS = ("-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+               "-Xcompiler", "-fPIC", "-shared")
+
+
+def _dep_files():
     srcs = [os.path.join(CSRC_DIR, s) for s in SOURCES if os.path.exists(os.path.join(CSRC_DIR, s))]
+    hdrs = sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith(".cuh"))
+    return srcs, hdrs + [os.path.join(INCLUDE_DIR, "dvc_b200.h")]
+
+
+def source_hash(extra=()):
+    """sha256[:16] of every CUDA source, header and the compiler flags: what
+    ``dvc_build_info()`` of a library built from this tree must report."""
+    import hashlib
+    h = hashlib.sha256()
+    srcs, hdrs = _dep_files()
+    for path in srcs + hdrs:
+        h.update(os.path.basename(path).encode() + b"\0")
+        h.update(open(path, "rb").read())
+    h.update(" ".join(_NVCC_FLAGS + tuple(e for e in extra if e not in ("-Xptxas", "-v"))).encode())
+    return h.hexdigest()[:16]
+
+
+def nvcc_command(out_path=LIB_PATH, extra=()):
+    srcs, _ = _dep_files()
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-lineinfo", "-Xcompiler", "-fPIC", "-shared", f"-I{INCLUDE_DIR}", f"-I{CSRC_DIR}",
-            *extra, "-o", out_path, *srcs]
+    return [nvcc, *_NVCC_FLAGS, f"-I{INCLUDE_DIR}", f"-I{CSRC_DIR}",
+            f'-DDVC_SRC_HASH="{source_hash(extra)}"', *extra, "-o", out_path, *srcs]
+
+
+def built_hash(path=None):
+    """The source hash recorded inside a built library (None if absent / unreadable)."""
+    import re
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        return None
+    # read the string out of the file instead of dlopen()ing it: a library that is about to
+    # be rebuilt must not already be mapped into this process
+    m = re.search(rb"src=([0-9a-f]{16}) arch=sm_100a", open(path, "rb").read())
+    return m.group(1).decode() if m else None
 
 
 def build_library(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into ``libdvc_b200.so`` (in-tree)."""
-    srcs = [os.path.join(CSRC_DIR, s) for s in SOURCES if os.path.exists(os.path.join(CSRC_DIR, s))]
-    deps = srcs + [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith(".cuh")]
-    deps.append(os.path.join(INCLUDE_DIR, "dvc_b200.h"))
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(d) for d in deps)
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+    # up to date = the hash compiled into the binary equals the hash of the sources on disk
+    # (mtimes do not survive a checkout or the copy to the GPU box)
+    if not force and built_hash() == source_hash():
+        return LIB_PATH
     cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
@@ -63,6 +94,7 @@ _lib = None
 _SIGNATURES = {
     "dvc_version": (c_int, []),
     "dvc_last_error_string": (c_char_p, []),
+    "dvc_build_info": (c_char_p, []),
     "dvc_device_info": (c_int, [POINTER(c_int)] * 3),
     "dvc_rate_workspace_bytes": (c_int64, [c_int64]),
     "dvc_flow_warp_fwd": (c_int, [c_void_p] * 3 + [c_int64] * 4 + [_P4] * 3 + [c_int, c_void_p]),

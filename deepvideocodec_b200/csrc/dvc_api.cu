@@ -53,6 +53,12 @@ extern "C" {
 
 int dvc_version(void) { return DVC_VERSION_NUMBER; }
 
+#ifndef DVC_SRC_HASH
+#define DVC_SRC_HASH "unknown"
+#endif
+// sha256 (first 16 hex digits) of the sources and compiler flags this binary was built from
+const char* dvc_build_info(void) { return "src=" DVC_SRC_HASH " arch=sm_100a"; }
+
 const char* dvc_last_error_string(void) { return dvc::g_err; }
 
 int dvc_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -49,6 +49,10 @@ enum {
 
 int dvc_version(void);                     /* MAJOR*10000 + MINOR*100 + PATCH */
 const char* dvc_last_error_string(void);   /* thread local, never NULL */
+/* "src=<sha256[:16] of csrc/ *.cu *.cuh, this header and the nvcc flags> arch=sm_100a": lets a
+ * reader check that a shipped (git-ignored) binary was built from the committed sources --
+ * `python -c "import deepvideocodec_b200 as d; print(d.source_hash(), d.lib().dvc_build_info())"`. */
+const char* dvc_build_info(void);
 /* Number of SMs / compute capability of the current device (diagnostics). */
 int dvc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -29,6 +29,14 @@ def test_header_cites_reference_interfaces():
     assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S).lower()
 
 
+def test_binary_matches_committed_sources():
+    """The shipped .so is git-ignored: it must say which sources it was built from."""
+    import deepvideocodec_b200 as dvc
+    info = dvc.lib().dvc_build_info().decode()
+    assert info.startswith("src=") and "sm_100a" in info
+    assert dvc.built_hash() == dvc.source_hash(), (info, dvc.source_hash())
+
+
 def test_version_and_sizes():
     import deepvideocodec_b200 as dvc
     lib = dvc.lib()
