@@ -20,6 +20,8 @@
 // separate torch ops use the *_rn helpers (never contracted); libdevice erfcf /
 // tanhf / expf / log1pf / logf and IEEE division are the same routines ATen's
 // CUDA kernels call.
+#include <stdlib.h>
+
 #include "dvc_common.cuh"
 
 namespace dvc {
@@ -329,9 +331,83 @@ struct StageBP {
   RateWS ws;
 };
 
+// kDense: every operand is a dense NCHW tensor (element (c,h,w) of a sample at c*H*W + h*W + w)
+// and the iteration space is mode 0 (one channel plane per blockIdx.y).  Then a thread's index
+// b IS the in-plane offset of every operand: the plane base pointers are per-block constants
+// and the per-element integer work is one multiply-high (h, for the checkerboard parity)
+// instead of seven 3-term stride products.  ncu on the strided version (r01): 230 warp
+// instructions per element, a third of them IMAD/ISETP of the offset arithmetic, at a 32-register
+// cap; this path is the one every contiguous latent takes (profiles/r02_gc_diet.md).
+template <bool kDense>
 __global__ void __launch_bounds__(kEThreads, 16) stage_b_gc_kernel(const StageBP p) {
   const int half = p.s.C >> 1;
   float lsum = 0.f;
+  if (kDense) {
+    const int n = blockIdx.z, c = blockIdx.y;
+    const int HW = p.s.B;
+    const bool second = c >= half;
+    const long long plane = (long long)c * HW;
+    const float* __restrict__ yb = p.y + n * p.ys.n + plane;
+    const float* __restrict__ mb = p.has_mean ? p.means + n * p.ms.n + plane : nullptr;
+    const float* __restrict__ sb = p.scales + n * p.ss.n + plane;
+    const float* __restrict__ nb = p.noise ? p.noise + n * p.ns.n + plane : nullptr;
+    // y_spatial_prior(params).chunk(4, 1) = (means_0, scales_0, means_1, scales_1)
+    const float* __restrict__ pmb = nullptr;
+    const float* __restrict__ psb = nullptr;
+    if (p.prior) {
+      const int cm = second ? (p.s.C + (c - half)) : c;
+      pmb = p.prior + n * p.prs.n + (long long)cm * HW;
+      psb = pmb + (long long)half * HW;
+    }
+    const long long ob = n * p.os.n + plane;
+    const long long hb = n * p.hs.n + (long long)(second ? c - half : c) * HW;
+    const int b_begin = blockIdx.x * p.s.per_block;
+    const int b_end = min(HW, b_begin + p.s.per_block);
+    for (int b0 = b_begin + threadIdx.x; b0 < b_end; b0 += kEThreads * kBatch) {
+      float y[kBatch], mu[kBatch], sg[kBatch], nz[kBatch];
+      bool fp[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int b = b0 + k * kEThreads;
+        fp[k] = true;
+        if (b < b_end) {
+          y[k] = __ldg(yb + b);
+          const float* pm = mb + b;
+          const float* ps = sb + b;
+          if (p.prior) {
+            const int h = p.s.magic ? (int)__umulhi((unsigned)b, p.s.magic) : b / p.s.W;
+            const int w = b - h * p.s.W;
+            fp[k] = (((h + w) & 1) != 0) == second;   // stage-A positions keep (means, scales)
+            if (!fp[k]) { pm = pmb + b; ps = psb + b; }
+          }
+          mu[k] = p.has_mean ? __ldg(pm) : 0.f;
+          sg[k] = __ldg(ps);
+          nz[k] = nb ? __ldg(nb + b) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int b = b0 + k * kEThreads;
+        if (b < b_end) {
+          const float q = rintf(p.has_mean ? sub_rn(y[k], mu[k]) : y[k]);
+          const float yh = p.has_mean ? add_rn(q, mu[k]) : q;
+          const float outv = nb ? add_rn(y[k], nz[k]) : yh;
+          const float pr = gc_prob(outv, mu[k], p.has_mean != 0, sg[k], p.scale_bound, p.lik_bound);
+          if (p.y_hat) p.y_hat[ob + b] = (p.prior || !nb) ? yh : outv;
+          if (p.means_hat) p.means_hat[ob + b] = mu[k];
+          if (p.scales_hat) p.scales_hat[ob + b] = sg[k];
+          if (p.lik) p.lik[ob + b] = pr;
+          if (p.q_w0) {  // mode='compress' planes (video_model.py:209-214)
+            if (fp[k]) { p.q_w0[hb + b] = q; p.s_w0[hb + b] = sg[k]; }
+            else       { p.q_w1[hb + b] = q; p.s_w1[hb + b] = sg[k]; }
+          }
+          lsum += logf(pr);
+        }
+      }
+    }
+    rate_commit(p.ws, blockIdx.z, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, lsum);
+    return;
+  }
   DVC_FOR_BATCH(p.s) {
     float y[kBatch], mu[kBatch], sg[kBatch], nz[kBatch];
     int oo[kBatch], oh[kBatch];
@@ -582,7 +658,24 @@ static int launch_stage_b(StageBP& p, int64_t N, double* logsum, void* workspace
                           cudaStream_t stream, const char* who) {
   int rc = rate_ws(p.ws, workspace, logsum, N);
   if (rc) return rc;
-  stage_b_gc_kernel<<<grid_of(p.s), kEThreads, 0, stream>>>(p);
+  // dense NCHW operands in plane-per-block enumeration -> the offset-free path
+  auto dense = [&](const TS& t, const void* ptr, int C) {
+    return !ptr || (t.w == 1 && t.h == p.s.W && t.c == p.s.H * p.s.W && C > 0);
+  };
+  const bool all_dense =
+      p.s.mode == 0 && dense(p.ys, p.y, p.s.C) && dense(p.ms, p.has_mean ? p.means : nullptr, p.s.C) &&
+      dense(p.ss, p.scales, p.s.C) && dense(p.prs, p.prior, 2 * p.s.C) && dense(p.ns, p.noise, p.s.C) &&
+      dense(p.os, (p.y_hat || p.means_hat || p.scales_hat || p.lik) ? (const void*)p.y : nullptr, p.s.C) &&
+      dense(p.hs, p.q_w0, p.s.C / 2);
+  static int use_dense = -1;   // tuning knob (not API): DVC_GC_DENSE=0 forces the strided path (A/B)
+  if (use_dense < 0) {
+    const char* e = getenv("DVC_GC_DENSE");
+    use_dense = e ? atoi(e) : 1;
+  }
+  if (all_dense && use_dense)
+    stage_b_gc_kernel<true><<<grid_of(p.s), kEThreads, 0, stream>>>(p);
+  else
+    stage_b_gc_kernel<false><<<grid_of(p.s), kEThreads, 0, stream>>>(p);
   return check_launch(who);
 }
 

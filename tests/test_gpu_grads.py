@@ -186,7 +186,7 @@ def test_entropy_bottleneck_backward(cuda_dev, training):
 
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("fmt", ["nchw", "nhwc"])
-def test_context_model_tail_backward(cuda_dev, training, fmt):
+def test_context_model_tail_backward(cuda_dev, training, fmt, monkeypatch):
     """dual prior (stage A -> conv -> stage B) + Gaussian conditional + rate,
     against reference ops + CompressAI restatement, gradients w.r.t. the
     latent, both priors and the conv weights."""
@@ -200,7 +200,7 @@ def test_context_model_tail_backward(cuda_dev, training, fmt):
     y, mu, sg = _latents(n, c, h, w, cuda_dev, g, mf)
     torch.manual_seed(58)
     conv = torch.nn.Conv2d(3 * c, 2 * c, 3, padding=1).to(cuda_dev)
-    torch.backends.cudnn.allow_tf32 = False
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # restored after the test
     gc_ref = oem.GaussianConditional(None).to(cuda_dev).train(training)
     gc = dvc.GaussianConditional(None).to(cuda_dev).train(training)
 
@@ -249,15 +249,15 @@ class _MiniMotionContext(torch.nn.Module):
 
 
 @pytest.mark.parametrize("training", [False, True])
-def test_motion_context_model_drop_in(cuda_dev, training):
+def test_motion_context_model_drop_in(cuda_dev, training, monkeypatch):
     """`MotionContextModel.forward` (video_model.py:218-233) restated with oracle
     ops vs the fused drop-in bound onto the same module: outputs, likelihoods,
     bpp and every parameter gradient."""
     import deepvideocodec_b200 as dvc
     from oracle import dmc_ref
     oem = _oracle_entropy_models()
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # restored after the test
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     c, cz = 16, 8
     torch.manual_seed(60)
     ref = _MiniMotionContext(c, cz, oem.EntropyBottleneck, oem.GaussianConditional).to(cuda_dev)
