@@ -453,8 +453,9 @@ def measure_extras(cx, paths, alg, peak, K, Wm, roofline):
                                                    regime=cx.args.regime, layout="nchw"), cx.ebs)
                 for s in range(N_SETS)]
     r = run(nchw)
-    r["kernel"] = ("warp_planar_kernel<staged> + <gather> per feature scale and warp_multi_kernel "
-                   "for x_ref: `kernel_ms` brackets all of them")
+    r["kernel"] = ("warp_planar_kernel<staged> (all three feature scales, one launch) + its "
+                   "complement launch <gather> + warp_multi_kernel for x_ref: `kernel_ms` brackets "
+                   "the three")
     r["launches_per_step"] = nchw[0].n_launches
     roofline["layouts"]["nchw"] = r
     del nchw

@@ -443,13 +443,30 @@ __device__ __forceinline__ void planar_planes(PlanarLoop& L, float* __restrict__
 #ifndef DVC_PLANAR_MINB
 #define DVC_PLANAR_MINB 4
 #endif
+// Up to kMaxTasks planar problems in ONE launch (largest first): the half- and quarter-resolution
+// context warps of a P-frame are 1.7 and 0.4 waves of CTAs on their own; laid behind the
+// full-resolution one they fill its tail instead of leaving the GPU half empty three times.
+struct PlanarBatch {
+  WarpTask t[kMaxTasks];
+  int n_tasks;
+  int first[kMaxTasks + 1];   // first block of each task; first[kMaxTasks] = number of planar blocks
+};
+
 template <bool kStaged>
 __global__ void __launch_bounds__(kThreads, DVC_PLANAR_MINB)
-warp_planar_kernel(const __grid_constant__ WarpTask t) {
+warp_planar_kernel(const __grid_constant__ PlanarBatch pb) {
   extern __shared__ __align__(16) float pl_smem[];
   __shared__ int s_red[32];   // static: the gather launch has no dynamic shared memory
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int tile = blockIdx.x;
+  // (Letting the 3-channel frame warp ride along in the complement launch was measured and
+  // dropped: 0.456-0.478 ms per NCHW step against 0.448 ms with its own warp_multi launch --
+  // it runs at this kernel's 64-register occupancy and the early-exit tiles are not free.)
+  int task = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxTasks; ++i)
+    if (i < pb.n_tasks && (int)blockIdx.x >= pb.first[i]) task = i;
+  const WarpTask& t = pb.t[task];
+  const int tile = blockIdx.x - pb.first[task];
   const int tx = tile % t.tiles_x;
   const int rest = tile / t.tiles_x;
   const int ty = rest % t.tiles_y;
@@ -803,37 +820,61 @@ static bool planar_ok(const WarpTask& t, const dvc_warp_task& in) {
          aligned16(in.im);
 }
 
-static int launch_planar(WarpTask t, const dvc_warp_task& in, cudaStream_t stream) {
+static void planar_tiles(WarpTask& t, const dvc_warp_task& in) {
   t.tiles_x = (int)((in.W + kPlTileW - 1) / kPlTileW);
   t.tiles_y = (int)((in.H + kPlTileH - 1) / kPlTileH);
-  const long long nb = (long long)t.tiles_x * t.tiles_y * in.N;
-  DVC_REQUIRE(nb < 2147483647LL, "flow_warp: too many tiles");
+  t.n_blocks = (int)((long long)t.tiles_x * t.tiles_y * in.N);
+}
+
+// one task through the TMA-staged kernel (+ its complement); only with DVC_WARP_PLANAR_TMA=1
+static int launch_planar_tma(WarpTask t, const PlanarMaps& maps, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_planar_tma_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (e != cudaSuccess)
+      return fail(DVC_ERR_CUDA, "flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  t.pl_tma = 1;
+  warp_planar_tma_kernel<<<(unsigned)t.n_blocks, kThreads, kTmaSmemBytes, stream>>>(t, maps);
+  int rc = check_launch("warp_planar_tma_kernel");
+  if (rc) return rc;
+  PlanarBatch pb;
+  pb.n_tasks = 1;
+  for (int i = 0; i < kMaxTasks; ++i) pb.t[i] = t;
+  pb.first[0] = 0;
+  for (int i = 1; i <= kMaxTasks; ++i) pb.first[i] = t.n_blocks;
+  warp_planar_kernel<false><<<(unsigned)t.n_blocks, kThreads, 0, stream>>>(pb);
+  return check_launch("warp_planar_kernel<gather>");
+}
+
+static int launch_planar_batch(PlanarBatch& pb, cudaStream_t stream) {
+  // largest task first
+  for (int i = 1; i < pb.n_tasks; ++i)
+    for (int j = i; j > 0 && pb.t[j].n_blocks > pb.t[j - 1].n_blocks; --j) {
+      const WarpTask tmp = pb.t[j];
+      pb.t[j] = pb.t[j - 1];
+      pb.t[j - 1] = tmp;
+    }
+  long long total = 0;
+  for (int i = 0; i < kMaxTasks; ++i) {
+    pb.first[i] = (int)total;
+    if (i < pb.n_tasks) total += pb.t[i].n_blocks;
+    else pb.t[i] = pb.t[0];
+  }
+  pb.first[kMaxTasks] = (int)total;
+  DVC_REQUIRE(total < 2147483647LL, "flow_warp: too many tiles");
   if (kPlSmemBytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(warp_planar_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmemBytes);
     if (e != cudaSuccess)
       return fail(DVC_ERR_CUDA, "flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  int rc;
-  PlanarMaps maps;
-  t.pl_tma = (planar_tma_mode() && build_planar_maps(maps, t, in)) ? 1 : 0;
-  if (t.pl_tma) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(warp_planar_tma_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
-      if (e != cudaSuccess)
-        return fail(DVC_ERR_CUDA, "flow_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
-    warp_planar_tma_kernel<<<(unsigned)nb, kThreads, kTmaSmemBytes, stream>>>(t, maps);
-    rc = check_launch("warp_planar_tma_kernel");
-  } else {
-    warp_planar_kernel<true><<<(unsigned)nb, kThreads, kPlSmemBytes, stream>>>(t);
-    rc = check_launch("warp_planar_kernel<staged>");
-  }
+  warp_planar_kernel<true><<<(unsigned)total, kThreads, kPlSmemBytes, stream>>>(pb);
+  int rc = check_launch("warp_planar_kernel<staged>");
   if (rc) return rc;
-  warp_planar_kernel<false><<<(unsigned)nb, kThreads, 0, stream>>>(t);
+  warp_planar_kernel<false><<<(unsigned)total, kThreads, 0, stream>>>(pb);
   return check_launch("warp_planar_kernel<gather>");
 }
 
@@ -899,6 +940,8 @@ static int launch_batch(const dvc_warp_task* tasks, int n_tasks, int flags,
   DVC_REQUIRE(tasks && n_tasks >= 1 && n_tasks <= kMaxTasks,
               "warp_multi: n_tasks must be in [1,%d]", kMaxTasks);
   WarpBatch batch;
+  PlanarBatch planar_batch;
+  planar_batch.n_tasks = 0;
   long long total = 0;
   int kept = 0;
   static int planar = -1;   // tuning knob (not API): DVC_WARP_PLANAR=0 keeps NCHW on the strided path
@@ -909,14 +952,29 @@ static int launch_batch(const dvc_warp_task* tasks, int n_tasks, int flags,
   for (int i = 0; i < n_tasks; ++i) {
     int rc = build_task(batch.t[kept], tasks[i], flags);
     if (rc) return rc;
-    if (planar && planar_ok(batch.t[kept], tasks[i])) {   // NCHW features: own launch
-      rc = launch_planar(batch.t[kept], tasks[i], stream);
-      if (rc) return rc;
+    if (planar && planar_ok(batch.t[kept], tasks[i])) {   // NCHW features: the staged kernels
+      WarpTask& pt = planar_batch.t[planar_batch.n_tasks];
+      pt = batch.t[kept];
+      pt.pl_tma = 0;
+      planar_tiles(pt, tasks[i]);
+      DVC_REQUIRE((long long)pt.tiles_x * pt.tiles_y * tasks[i].N < 2147483647LL,
+                  "flow_warp: too many tiles");
+      PlanarMaps maps;
+      if (planar_tma_mode() && build_planar_maps(maps, pt, tasks[i])) {
+        rc = launch_planar_tma(pt, maps, stream);
+        if (rc) return rc;
+      } else {
+        ++planar_batch.n_tasks;
+      }
       continue;
     }
     batch.t[kept].first_block = (int)total;
     total += batch.t[kept].n_blocks;
     ++kept;
+  }
+  if (planar_batch.n_tasks > 0) {
+    int rc = launch_planar_batch(planar_batch, stream);
+    if (rc) return rc;
   }
   n_tasks = kept;
   batch.n_tasks = n_tasks;

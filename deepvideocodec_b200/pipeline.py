@@ -312,12 +312,12 @@ class PFramePath:
     @property
     def n_launches(self):
         """Kernel launches of one ``launch()``.  NCHW (non channels_last) feature
-        scales take the staged planar path: two launches per scale (the staged
-        tiles and their complement) instead of a share of the one multi-scale
-        launch."""
-        planar = sum(1 for k in (1, 2, 3)
-                     if self.inp[f"feat{k}"].is_contiguous() and self.inp[f"feat{k}"].size(1) >= 8)
-        return len(self._pre_calls) + 1 + 2 * planar + len(self._ent_calls) + 1
+        scales take the staged planar path: one launch for the staged tiles of
+        all scales and one for their complement, beside the multi-scale launch
+        that keeps the 3-channel frame."""
+        planar = any(self.inp[f"feat{k}"].is_contiguous() and self.inp[f"feat{k}"].size(1) >= 8
+                     for k in (1, 2, 3))
+        return len(self._pre_calls) + 1 + (2 if planar else 0) + len(self._ent_calls) + 1
 
 
 class SpyNetWarps:

@@ -219,3 +219,50 @@ def test_planar_nchw_kernel_bit_identical(cuda_dev, shape, regime):
     wide = torch.randn(n, c, h, w + 8, device=cuda_dev, generator=g)
     view = wide[..., 4:4 + w]
     assert torch.equal(dvc.flow_warp(view, flow), dmc_ref.flow_warp(view.contiguous(), flow))
+
+
+@pytest.mark.parametrize("hw", [(2160, 3840), (2176, 3840)], ids=["4k", "4k_padded"])
+def test_flow_warp_4k_config5(cuda_dev, hw):
+    """BASELINE.json configs[4]: flow_warp at 3840x2160 (and the x64-padded 3840x2176),
+    C in {3, 64}, NCHW and channels_last: bit-identical to CUDA eager, and one
+    size-independent property -- a constant integer flow is an exact shift."""
+    import deepvideocodec_b200 as dvc
+    from oracle import dmc_ref
+    h, w = hw
+    g = torch.Generator(device=cuda_dev).manual_seed(h)
+    flow = _smooth_flow(1, h, w, 4.0, cuda_dev, g)
+    for c, fmt in ((3, torch.contiguous_format), (64, torch.channels_last), (64, torch.contiguous_format)):
+        im = torch.randn(1, c, h, w, device=cuda_dev, generator=g).contiguous(memory_format=fmt)
+        out = dvc.flow_warp(im, flow)
+        ref = dmc_ref.flow_warp(im, flow)
+        assert (out - ref).abs().max().item() <= WARP_ATOL, (c, fmt)
+        assert (out == ref).float().mean().item() >= 0.999
+        del ref
+        shift = torch.zeros(1, 2, h, w, device=cuda_dev)
+        shift[:, 0] = 3.0
+        shift[:, 1] = -2.0
+        moved = dvc.flow_warp(im, shift)
+        # interior: out[h, w] = im[h - 2, w + 3] up to the reference's own coordinate rounding
+        a = moved[:, :, 8:-8, 8:-8]
+        b = im[:, :, 6:-10, 11:-5]
+        assert (a - b).abs().max().item() <= 2e-3 * im.abs().max().item()
+        del im, out, moved
+
+
+def test_motion_compensation_nchw_one_launch_pair(cuda_dev):
+    """The three NCHW context scales of a P-frame go through ONE staged launch and ONE
+    complement launch (batched planar tasks): same bits as three separate warps."""
+    import deepvideocodec_b200 as dvc
+    from oracle import dmc_ref
+    g = torch.Generator(device=cuda_dev).manual_seed(91)
+    h, w = 272, 480
+    x_ref = torch.rand(1, 3, h, w, device=cuda_dev, generator=g)
+    f1 = torch.randn(1, 64, h, w, device=cuda_dev, generator=g)
+    f2 = torch.randn(1, 64, h // 2, w // 2, device=cuda_dev, generator=g)
+    f3 = torch.randn(1, 64, h // 4, w // 4, device=cuda_dev, generator=g)
+    for mv in (_smooth_flow(1, h, w, 4.0, cuda_dev, g),
+               torch.randn(1, 2, h, w, device=cuda_dev, generator=g) * 16):
+        got = dvc.motion_compensation_warps(x_ref, f1, f2, f3, mv)
+        want = dmc_ref.motion_compensation_warps(x_ref, f1, f2, f3, mv)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
