@@ -15,6 +15,7 @@ from .context import (dual_prior_stage_a, dual_prior_stage_b_gc, forward_dual_pr
 from . import coder  # noqa: F401
 from .entropy_models import (EntropyBottleneck, EntropyModel, GaussianConditional,  # noqa: F401
                              LowerBound)
+from .graph import GraphedInter  # noqa: F401
 from .layers import (bilineardownsacling, flow_pyramid, flow_warp,  # noqa: F401
                      motion_compensation_warps, pack_conv3x3_weight, torch_warp, warp_conv3x3,
                      warp_multi)

@@ -98,9 +98,29 @@ def _set(obj, name, value):
     setattr(obj, name, value)
 
 
-def patch(models_pkg, train_module=None, fuse_context_models=True, fuse_warp_conv=False):
+def _graphed_forward_inter(eager_inter):
+    """``DMC.forward_inter`` replayed from one CUDA graph per P-frame in inference
+    (``graph.GraphedInter``); the eager method everywhere else."""
+    from .graph import GraphedInter
+
+    def forward_inter(self, x_cur, dpb, motion_pretrain=False, frame_pretrain=False):
+        g = self.__dict__.get("_dvc_graphed_inter")
+        if g is None:
+            g = GraphedInter(self, eager_inter=eager_inter)
+            self.__dict__["_dvc_graphed_inter"] = g
+        return g(x_cur, dpb, motion_pretrain, frame_pretrain)
+    return forward_inter
+
+
+def patch(models_pkg, train_module=None, fuse_context_models=True, fuse_warp_conv=False,
+          graph_inter=False):
     """Rebind the hot-path names of the reference ``models`` package (the
-    module object of ``dmc/models``).  Idempotent; ``unpatch()`` restores."""
+    module object of ``dmc/models``).  Idempotent; ``unpatch()`` restores.
+
+    ``graph_inter=True`` additionally replays ``DMC.forward_inter`` from one CUDA
+    graph per P-frame whenever the model is in eval mode under ``no_grad``
+    (2.9x at 256x256, 1.09x at 1080p on the reference's own
+    model)."""
     if _saved:
         return
     vm = sys.modules[models_pkg.__name__ + ".video_model"]
@@ -124,6 +144,8 @@ def patch(models_pkg, train_module=None, fuse_context_models=True, fuse_warp_con
         _set(vm.FrameContextModel, "decompress", context.frame_context_decompress)
     _set(vm.DMC, "motion_compensation",
          motion_compensation_fused if fuse_warp_conv else _motion_compensation)
+    if graph_inter:
+        _set(vm.DMC, "forward_inter", _graphed_forward_inter(vm.DMC.forward_inter))
     if train_module is not None:
         _set(train_module, "collect_likelihoods_list", rate.collect_likelihoods_list)
 

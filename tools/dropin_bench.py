@@ -135,6 +135,17 @@ def main():
                     del graph, g_out, eager_out
                 except Exception as e:  # noqa: BLE001
                     arm["patched_graph_error"] = repr(e)[:400]
+                # ---- the shipped form of it: dvc.GraphedInter (copies in, clones out) -----------
+                try:
+                    gi = dvc.GraphedInter(patched)
+                    dpb = populated_dpb(patched, fr)
+                    fn = lambda d=dpb: gi(fr[2], d)  # noqa: E731
+                    ref_out = patched.forward_inter(fr[2], dpb)
+                    arm["graphed_inter_x_hat_equal"] = bool(torch.equal(fn()[0], ref_out[0]))
+                    arm["graphed_inter_ms"] = timeit(fn, args.iters, args.warm)
+                    del gi, ref_out
+                except Exception as e:  # noqa: BLE001
+                    arm["graphed_inter_error"] = repr(e)[:400]
                 # ---- warp fused into its 3x3 conv (row f3, opt-in) ----------------------
                 try:
                     dvc.unpatch()
@@ -150,6 +161,8 @@ def main():
             arm["speedup_patched"] = arm["stock_eager_ms"] / arm["patched_ms"]
             if "patched_graph_ms" in arm:
                 arm["speedup_patched_graph"] = arm["stock_eager_ms"] / arm["patched_graph_ms"]
+            if "graphed_inter_ms" in arm:
+                arm["speedup_graphed_inter"] = arm["stock_eager_ms"] / arm["graphed_inter_ms"]
             res["arms"][tag] = arm
             print(tag, json.dumps(arm), flush=True)
             torch.cuda.empty_cache()
