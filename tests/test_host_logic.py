@@ -199,3 +199,58 @@ def test_bench_reference_arm_line():
     assert line["impl"] == "reference" and line["unit"] == "P-frames/s"
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["frame"] == [1088, 1920]
+
+
+def test_substream_policy_follows_the_payload():
+    """coder.auto_stream_symbols (pure host logic): <= 1 % container overhead, a floor of
+    MIN_STREAMS sub-streams, whole 256-symbol chunks, pinned lengths win."""
+    from deepvideocodec_b200 import coder
+    L = 48 * 68 * 120
+    assert coder.auto_stream_symbols(L, None) == coder.DEFAULT_STREAM_SYMBOLS
+    for est in (50.0, 2_000.0, 50_000.0, 400_000.0):
+        S = coder.auto_stream_symbols(L, est)
+        n = (L + S - 1) // S
+        assert S % 256 == 0 and S >= coder.MIN_STREAM_SYMBOLS
+        assert n >= min(coder.MIN_STREAMS, (L + 255) // 256) - 1
+        if n > coder.MIN_STREAMS:                      # above the floor the 1 % target binds
+            assert n * coder.STREAM_OVERHEAD_BYTES <= coder.OVERHEAD_TARGET * est + 12
+    # more payload -> more sub-streams (faster), never fewer
+    sizes = [coder.auto_stream_symbols(L, e) for e in (1e3, 1e4, 1e5, 1e6)]
+    assert sizes == sorted(sizes, reverse=True) and sizes[-1] < 4096 < sizes[0]
+    saved = coder.PINNED_STREAM_SYMBOLS
+    try:
+        coder.PINNED_STREAM_SYMBOLS = 0
+        assert coder.auto_stream_symbols(L, 1e6) == 0     # interop: one raw stock stream
+    finally:
+        coder.PINNED_STREAM_SYMBOLS = saved
+
+
+def test_reference_loads_twice_stock_and_patched():
+    """oracle/load_reference.py: the unmodified reference as two independent packages in one
+    process (stock over the eager restatement, patched over this package's modules), identical
+    state-dict layouts, `patch` rebinding only the patched copy -- the setup of
+    tests/test_gpu_dropin.py, checked here without a GPU."""
+    from oracle.load_reference import load_stock_and_patched, reference_available
+    if not reference_available():
+        pytest.skip("reference not present")
+    import deepvideocodec_b200 as dvc
+    stock_pkg, patched_pkg = load_stock_and_patched()
+    try:
+        assert "compressai" not in sys.modules or not getattr(sys.modules["compressai"], "__file__", "").startswith(ROOT)
+        vm_s = sys.modules["dvc_ref_stock.video_model"]
+        vm_p = sys.modules["dvc_ref_patched.video_model"]
+        assert vm_p.flow_warp is dvc.flow_warp and vm_s.flow_warp is not dvc.flow_warp
+        assert vm_s.flow_warp.__module__ == "dvc_ref_stock.layers"
+        torch.manual_seed(0)
+        a, b = stock_pkg.DMC(), patched_pkg.DMC()
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and len(sa) == 438                # SURVEY.md 8c
+        assert sum(p.numel() for p in a.parameters()) == 16884403
+        b.load_state_dict(sa)
+        assert type(b.motion_context_model.entropy_bottleneck).__module__ == \
+            "deepvideocodec_b200.entropy_models"
+        assert type(a.motion_context_model.entropy_bottleneck).__module__.startswith("compressai")
+        with pytest.raises(dvc.DvcError):                             # no CPU fallback
+            b([torch.zeros(1, 3, 64, 64)] * 2)
+    finally:
+        dvc.unpatch()
