@@ -679,7 +679,8 @@ def run_gop(cx):
     units = make_units([96] * n_seq)
     mine = shard_units(units, cx.rank, cx.world)
     runner = GopRunner(H, W, cx.dev, cx.ebs, regime=cx.args.regime)
-    runner.run_units(mine[:1])                                   # warm-up: one unit
+    warm = runner.run_units(mine[:1])                            # warm-up: one unit ...
+    reduce_stats(warm, device=cx.dev)                            # ... and one collective (lazy NCCL init)
     cx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(cx.local)

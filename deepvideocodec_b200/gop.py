@@ -13,10 +13,11 @@ unit the warped frame and the three warped contexts of P-frame ``t`` ARE the
 ``x_ref`` / feature pyramid of P-frame ``t + 1`` (two ``PFramePath`` objects
 write into each other's dpb buffers -- no copy), the frame-dependent inputs
 (motion field, latents, priors; conv outputs in the codec) rotate through a
-pool of resident synthetic sets, and each frame's bits land in row ``t`` of a
-per-unit fp64 table on the device.  Nothing is read back until the unit ends;
-the per-rank accumulators go through ``dist.reduce_stats`` (ONE all-reduce of
-four fp64 words per report -- NCCL on the box).
+pool of resident synthetic sets, and each frame's bits land in element ``t`` of
+the unit's row of an fp64 table on the device.  ``run_units`` enqueues all units
+without a host synchronisation and reads the table back once; the per-rank
+accumulators go through ``dist.reduce_stats`` (ONE all-reduce of four fp64 words
+per report -- NCCL on the box).
 """
 import torch
 
@@ -60,6 +61,7 @@ class GopRunner:
                 inp = dict(self.dpb[p])
                 inp.update(self.frames[s])
                 self.paths[(p, s)] = PFramePath(inp, eb_modules, outputs=outs)
+        self.max_frames = max_frames
         self.bits = torch.zeros((max_frames, 1), dtype=torch.float64, device=device)
         self._g = torch.Generator(device=device)
 
@@ -73,29 +75,33 @@ class GopRunner:
         for k in ("feat1", "feat2", "feat3"):
             d[k].normal_(0.0, 1.0, generator=self._g)
 
-    def launch_unit(self, unit: Unit):
+    def launch_unit(self, unit: Unit, bits=None):
         """Enqueue every P-frame of ``unit`` (no host synchronisation); returns
-        the number of P-frames enqueued.  ``self.bits[:n]`` holds their bits once
-        the stream has drained."""
+        the number of P-frames enqueued.  ``bits[:n]`` (default ``self.bits``)
+        holds their bits once the stream has drained."""
+        bits = self.bits if bits is None else bits
         n = unit.p_frames
-        if n > self.bits.size(0):
-            raise nat.DvcError(f"unit of {n} P-frames exceeds max_frames={self.bits.size(0)}")
+        if n > bits.size(0):
+            raise nat.DvcError(f"unit of {n} P-frames exceeds the bits table ({bits.size(0)} rows)")
         self._reset_dpb(unit)
-        base = self.bits.data_ptr()
+        base = bits.data_ptr()
         for t in range(n):
             self.paths[(t & 1, t % self.frame_pool)].launch(bits_ptr=base + 8 * t)
         return n
 
     def run_units(self, units, stats=None):
-        """Run units back to back; one D2H read of the bits table per unit.
+        """Run units back to back with NO host synchronisation in between: every
+        unit gets its own rows of one device table, read back once at the end.
         Returns ``RateStats`` (bits, frames, pixels accumulated in fp64)."""
         stats = stats or RateStats()
-        for u in units:
-            n = self.launch_unit(u)
-            if n == 0:
-                continue
-            per_frame = self.bits[:n, 0].cpu().tolist()      # synchronises: the unit is done
-            for b in per_frame:
+        units = list(units)
+        if not units:
+            return stats
+        table = torch.zeros((len(units), self.max_frames), dtype=torch.float64, device=self.device)
+        counts = [self.launch_unit(u, table[i].unsqueeze(1)) for i, u in enumerate(units)]
+        host = table.cpu()                                   # the only synchronisation
+        for i, n in enumerate(counts):
+            for b in host[i, :n].tolist():                   # fixed order: deterministic fp64 sum
                 stats.bits += b
             stats.frames += n
             stats.pixels += float(n * self.h * self.w)
