@@ -139,10 +139,17 @@ def test_entropy_bottleneck_eval(cuda_dev, shape, fmt, spread):
     assert torch.equal(o_out, r_out)
     assert torch.equal(o_zhat, r_zhat)
     rel = ((o_lik - r_lik).abs() / r_lik)
-    # cuBLAS bmm (K<=3) accumulation order is opaque: allow the documented
-    # fp32 conditioning of the reference itself on a tiny tail
-    assert rel.max().item() <= 5e-5, rel.max().item()
-    assert (rel > LIK_RTOL).float().mean().item() <= 1e-3
+    # Eager's last logits product ([C,1,3] @ [C,3,N]) changes its rounding order with the
+    # problem size (tools/eb_probe.py, profiles/r02_eb_probe.json): from ~21k columns x
+    # channels up -- every 1080p / 4K hyper-latent -- cuBLAS runs the ascending FMA chain the
+    # kernel replays, and the likelihoods are BIT-IDENTICAL; below that it uses two other
+    # orders and a small tail differs inside the fp32 conditioning of the formula.
+    columns = shape[0] * shape[2] * shape[3]
+    if shape[1] * columns >= 32000:
+        assert torch.equal(o_lik, r_lik), rel.max().item()
+    else:
+        assert rel.max().item() <= 5e-5, rel.max().item()
+        assert (rel > LIK_RTOL).float().mean().item() <= 1e-3
     ref_bits = -torch.log2(r_lik.double()).sum(dim=(1, 2, 3))
     bits = -o_lik._dvc_logsum / math.log(2)
     assert _rel_err(bits, ref_bits) <= BITS_RTOL
