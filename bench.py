@@ -276,23 +276,31 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
+EVENT_EVERY = 4     # the dominant kernel is bracketed by CUDA events on every 4th step
+
+
 def time_steps(cx, step, K, Wm, warp_events=False):
     """W warm-ups, then K steps between barriers; CUDA events on the launch
-    stream; max over ranks.  ``step(i, events_or_None)`` enqueues step i."""
+    stream; max over ranks.  ``step(i, events_or_None)`` enqueues step i.
+
+    The dominant kernel's duration is measured live inside the timed region, on
+    every ``EVENT_EVERY``-th step: an event pair around every launch costs 3-4 % of
+    the step (tools/host_overhead.py: 262 -> 273 us at K = 400) because each record
+    is a command of its own between the kernels of two streams."""
     torch = cx.torch
     for i in range(Wm):
         step(i, None)
     cx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(K)] if warp_events else None
+    wev = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for i in range(0, K, EVENT_EVERY)} if warp_events else {}
     ev0.record()
     for i in range(K):
-        step(i, wev[i] if wev else None)
+        step(i, wev.get(i))
     ev1.record()
     cx.barrier()
     ms = cx.max_over_ranks(ev0.elapsed_time(ev1))
-    warp_ms = sum(a.elapsed_time(b) for a, b in wev) / K if wev else None
+    warp_ms = sum(a.elapsed_time(b) for a, b in wev.values()) / len(wev) if wev else None
     return ms, warp_ms
 
 
@@ -346,7 +354,10 @@ def main():
                 "traffic": load_traffic(),
                 "traffic_source": "static: one `ncu --set full` capture of this kernel, committed "
                                   "as profiles/warp_multi_traffic.json (not re-measured by this run)",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["warp_multi"]}
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["warp_multi"],
+                "kernel_ms_samples": len(range(0, K, EVENT_EVERY)),
+                "kernel_ms_note": f"CUDA-event pairs around the kernel on every {EVENT_EVERY}th step "
+                                  "of the timed region"}
     whole = {"algorithmic_bytes": step_bytes,
              "algorithmic_bytes_incl_pyramid": alg["total"],
              "note": "the fused path derives mv2/mv3 inside the warp kernel, so the 26.1 MB of "
