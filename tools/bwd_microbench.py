@@ -93,6 +93,8 @@ def main():
         out["rows"].append(row("flow_warp backward", (n, c, h, w, fmt), alg, time_bwd(ours),
                                time_bwd(eager, 6, 2)))
         del im, flow, go
+    if os.environ.get("ONLY_WARP"):
+        return
     # ---- flow pyramid backward ------------------------------------------------------------
     mv = randn(8, 2, 256, 256).requires_grad_(True)
     go = randn(8, 2, 128, 128)
