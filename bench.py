@@ -353,7 +353,8 @@ def main():
                 **frac_of(alg["warp_multi"], warp_ms), "peak": peak, "unit": "GB/s",
                 "traffic": load_traffic(),
                 "traffic_source": "static: one `ncu --set full` capture of this kernel, committed "
-                                  "as profiles/warp_multi_traffic.json (not re-measured by this run)",
+                                  "as profiles/r02_warp_multi_traffic.json (not re-measured by this "
+                                  "run)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["warp_multi"],
                 "kernel_ms_samples": len(range(0, K, EVENT_EVERY)),
                 "kernel_ms_note": f"CUDA-event pairs around the kernel on every {EVENT_EVERY}th step "
@@ -409,12 +410,13 @@ def main():
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu
     capture (profiles/*traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "warp_multi_traffic.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["dram_bytes_per_launch"])
-        except Exception:  # noqa: BLE001
-            return None
+    for name in ("r02_warp_multi_traffic.json", "warp_multi_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                return float(json.load(open(p))["dram_bytes_per_launch"])
+            except Exception:  # noqa: BLE001
+                continue
     return None
 
 

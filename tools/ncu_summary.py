@@ -33,7 +33,10 @@ def launches(path, out):
     tot = defaultdict(list)
     for r in rows[hi + 1:]:
         if len(r) > vi:
-            tot[r[ki].split("(")[0]].append(float(r[vi].replace(",", "")))
+            name = r[ki].split("(")[0]
+            if name.startswith("void "):            # template instantiations print their return type
+                name = name[5:]
+            tot[name].append(float(r[vi].replace(",", "")))
     ours = {k: v for k, v in tot.items() if k.startswith("dvc::")}
     s = sum(sum(v) for v in ours.values())
     with open(out, "w") as f:
