@@ -23,11 +23,19 @@ import torch
 
 from . import _native as nat
 
-__all__ = ["DEFAULT_STREAM_SYMBOLS", "PINNED_STREAM_SYMBOLS", "MAGIC", "PendingStreams", "auto_stream_symbols", "build_indexes", "collect",
+__all__ = ["DEFAULT_STREAM_SYMBOLS", "PINNED_STREAM_SYMBOLS", "MAGIC", "MAGIC_LANES", "MAGIC_LANES_SKIP",
+           "DEFAULT_LANES", "DEFAULT_SKIP", "SKIP_MIN_FREQ", "PendingStreams", "auto_stream_symbols",
+           "build_indexes", "check_decode_status", "collect", "container_of",
            "decode_stage_a", "decode_stage_b", "pmf_to_quantized_cdf", "quantize_symbols",
            "rans_decode", "rans_encode", "rans_encode_async", "stream_symbols_of"]
 
-MAGIC = 0x31435644                     # "DVC1"
+MAGIC = 0x31435644                     # "DVC1": one stock rans64 stream per sub-stream (lanes = 1)
+MAGIC_LANES = 0x33435644               # "DVC3": 32 lane-interleaved rans64 coders per sub-stream
+MAGIC_LANES_SKIP = 0x33535644          # "DVS3": "DVC3" + implied zeros (group flags)
+SKIP_MIN_FREQ = (1 << 16) - 8          # a table row is marked when value 0 holds this much mass
+# Layout of the container (stream_symbols > 0): 32 = lane-interleaved (default), 1 = 'DVC1'
+DEFAULT_LANES = int(os.environ.get("DVC_RANS_LANES", "32"))
+DEFAULT_SKIP = os.environ.get("DVC_RANS_SKIP", "1") != "0"
 _ENV_S = os.environ.get("DVC_RANS_STREAM_SYMBOLS")
 # Sub-stream length when nothing is known about the payload (module-level compress()):
 DEFAULT_STREAM_SYMBOLS = int(_ENV_S) if _ENV_S is not None else 4096
@@ -36,10 +44,13 @@ PINNED_STREAM_SYMBOLS = int(_ENV_S) if _ENV_S is not None else None
 MIN_STREAMS = int(os.environ.get("DVC_RANS_MIN_STREAMS", "8"))
 MIN_STREAM_SYMBOLS = 256
 STREAM_OVERHEAD_BYTES = 12             # per sub-stream: 4 B length word + 8 B rans64 flush
+LANES_OVERHEAD_BYTES = 200             # lanes = 32: length + mask words + 32 states of 1-2 words
+LANES_STREAM_SYMBOLS = 65536           # lanes = 32, payload unknown: 2 048 rounds per sub-stream
+LANES_CHUNK = 1024                     # positions per chunk of the lane-interleaved kernels
 OVERHEAD_TARGET = float(os.environ.get("DVC_RANS_OVERHEAD", "0.01"))
 
 
-def auto_stream_symbols(n_symbols, est_bytes=None):
+def auto_stream_symbols(n_symbols, est_bytes=None, lanes=1):
     """Sub-stream length used when the caller does not choose one.
 
     Range coding is serial inside a sub-stream, so a launch lasts
@@ -59,6 +70,14 @@ def auto_stream_symbols(n_symbols, est_bytes=None):
     recorded in the container header, so decoders need no matching policy."""
     if PINNED_STREAM_SYMBOLS is not None:
         return PINNED_STREAM_SYMBOLS
+    if lanes == 32 and DEFAULT_STREAM_SYMBOLS > 0:
+        # 32 chains per sub-stream for ~200 bytes: the sub-stream count follows the payload
+        # (>= 1: one warp, n_symbols / 32 rounds -- and far fewer with implied zeros)
+        if est_bytes is None:
+            return LANES_STREAM_SYMBOLS
+        n = max(1, int(OVERHEAD_TARGET * float(est_bytes) // LANES_OVERHEAD_BYTES))
+        s = (n_symbols + n - 1) // n
+        return max(LANES_CHUNK, (s + LANES_CHUNK - 1) // LANES_CHUNK * LANES_CHUNK)
     if est_bytes is None or DEFAULT_STREAM_SYMBOLS <= 0:
         return DEFAULT_STREAM_SYMBOLS
     n = int(OVERHEAD_TARGET * float(est_bytes) // STREAM_OVERHEAD_BYTES)
@@ -107,6 +126,57 @@ class Tables:
         self.offset = _dev_i32(offset, "_offset")
         if self.size.numel() != self.cdf.size(0) or self.offset.numel() != self.cdf.size(0):
             raise ValueError("CDF tables disagree on the number of distributions")
+
+    def skip_rows(self):
+        """uint8 ``[n_cdf]`` on the device: 1 where value 0 (table position
+        ``-offset``) holds at least ``SKIP_MIN_FREQ`` / 65536 of the row's mass.
+        Encoder and decoder derive it from the tables; symbols of such rows are
+        coded as one flag per group of 32 positions (``DVS3``, include/dvc_b200.h).
+        Cached on the CDF buffer, keyed on the buffers' versions."""
+        key = (self.cdf._version, self.size.data_ptr(), self.size._version,
+               self.offset.data_ptr(), self.offset._version)
+        hit = getattr(self.cdf, "_dvc_skip_rows", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        n = self.cdf.size(0)
+        pos = (-self.offset).long()
+        ok = (pos >= 0) & (pos < (self.size.long() - 2))
+        p = pos.clamp(0, self.cdf.size(1) - 2)
+        rows = torch.arange(n, device=self.cdf.device)
+        freq = self.cdf[rows, p + 1] - self.cdf[rows, p]
+        marks = (ok & (freq >= SKIP_MIN_FREQ)).to(torch.uint8).contiguous()
+        try:
+            self.cdf._dvc_skip_rows = (key, marks)
+        except AttributeError:
+            pass
+        return marks
+
+    def cdf_lut(self):
+        """int16 ``[n_cdf, 65]`` on the device (read as uint16 by the kernel), or
+        ``None`` for tables the kernel does not stage (more than 256 rows, rows
+        longer than 32 767): ``lut[r, b] = max j with cdf[r, j] <= 1024 b`` for
+        ``b < 64``, ``lut[r, 64] = cdf_length[r] - 2``.  It brackets the decoder's
+        CDF search (``dvc_rans_decode(cdf_lut)``) and never changes a result.
+        Cached on the CDF buffer like ``skip_rows``."""
+        key = (self.cdf._version, self.size.data_ptr(), self.size._version)
+        hit = getattr(self.cdf, "_dvc_cdf_lut", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        n, width = self.cdf.shape
+        lut = None
+        if n <= 256 and width <= 32767:
+            cols = torch.arange(width, device=self.cdf.device)
+            rows = torch.where(cols[None, :] < self.size[:, None].long(), self.cdf,
+                               torch.full_like(self.cdf, 1 << 17))          # sorted rows
+            thr = (torch.arange(64, device=self.cdf.device, dtype=torch.int32) * 1024)
+            idx = torch.searchsorted(rows, thr.expand(n, 64).contiguous(), right=True) - 1
+            lut = torch.cat((idx.to(torch.int32), (self.size - 2)[:, None]), 1)
+            lut = lut.clamp_(min=0).to(torch.int16).contiguous()
+        try:
+            self.cdf._dvc_cdf_lut = (key, lut)
+        except AttributeError:
+            pass
+        return lut
 
 
 def pmf_to_quantized_cdf(pmf, precision=16):
@@ -204,7 +274,7 @@ class PendingStreams:
 
 def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, scales=None,
                       scale_table=None, scale_bound=0.11, stream_symbols=None, overlap=False,
-                      est_bytes=None):
+                      est_bytes=None, lanes=None, skip=None):
     """Launch the encoder for one tensor ``[N,C,H,W]``; no host synchronisation.
 
     Symbols: ``symbols`` (int32) or ``round(x - means)``.  Table indexes:
@@ -214,6 +284,14 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
 
     ``est_bytes``: estimated coded size of ONE sample (``-sum log2 p / 8``), used by
     ``auto_stream_symbols`` to bound the container overhead.
+
+    ``lanes`` (default ``DVC_RANS_LANES`` = 32): 32 = every sub-stream is coded by
+    32 lane-interleaved rans64 coders (``DVC3``), 1 = one stock stream per
+    sub-stream (``DVC1``).  ``skip`` (default ``DVC_RANS_SKIP`` = on; lanes = 32
+    only): symbols of (almost) deterministic table rows are coded as one flag per
+    group of 32 (``DVS3``), which shortens the serial chain by up to 32x on them --
+    most of a low-rate P-frame.  Both are ignored for a raw stock stream
+    (``stream_symbols == 0``); all layouts are lossless.
 
     ``overlap=True`` runs the encoder on a per-device side stream (ordered after
     everything already queued on the current stream): the coder keeps a handful
@@ -237,11 +315,22 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
         symbols = symbols.to(torch.int32).contiguous()
     ip, sp, tp, T, sst, keep = _index_args(indexes, scales, scale_table, src.shape, dev)
     L = c * h * w
+    lanes = DEFAULT_LANES if lanes is None else int(lanes)
+    if lanes not in (1, 32):
+        raise ValueError("lanes must be 1 or 32")
     if stream_symbols is None:
-        stream_symbols = auto_stream_symbols(L, est_bytes)   # est_bytes: per sample
+        stream_symbols = auto_stream_symbols(L, est_bytes, lanes)   # est_bytes: per sample
+    if int(stream_symbols) <= 0:
+        lanes = 1                                   # raw stock stream
+    if lanes == 32:                                 # sub-streams are whole chunks of 1 024 positions
+        stream_symbols = -(-int(stream_symbols) // LANES_CHUNK) * LANES_CHUNK
+    skip = (DEFAULT_SKIP if skip is None else bool(skip)) and lanes == 32
+    marks = tables.skip_rows() if skip else None
+    if marks is not None:
+        keep = keep + [marks]
     lib = nat.lib()
-    cap = lib.dvc_rans_max_bytes(L, int(stream_symbols))
-    scratch_bytes = lib.dvc_rans_scratch_bytes(n, L, int(stream_symbols))
+    cap = lib.dvc_rans_max_bytes(L, int(stream_symbols), lanes)
+    scratch_bytes = lib.dvc_rans_scratch_bytes(n, L, int(stream_symbols), lanes)
     if cap < 0 or scratch_bytes < 0:
         raise nat.DvcError(f"rans_encode: unsupported partition (L={L}, S={stream_symbols})")
     out = torch.empty((n, cap), dtype=torch.uint8, device=dev)
@@ -260,7 +349,7 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
             tables.cdf.data_ptr(), tables.size.data_ptr(), tables.offset.data_ptr(),
             tables.cdf.size(0), tables.cdf.size(1), out.data_ptr(), cap, out_bytes.data_ptr(),
             scratch.data_ptr(), status.data_ptr(), n, c, h, w, nat.opt_st4(x),
-            nat.opt_st4(means), sst, int(stream_symbols), stream)
+            nat.opt_st4(means), sst, int(stream_symbols), lanes, nat.ptr(marks), stream)
         if overlap:
             done = torch.cuda.Event()
             done.record(side)
@@ -314,20 +403,46 @@ def rans_encode(tables, **kwargs):
 
 def stream_symbols_of(string, n_symbols):
     """Sub-stream length a bit stream was written with (0 = raw stock stream)."""
+    return container_of(string, n_symbols)[0]
+
+
+def container_of(string, n_symbols):
+    """``(stream_symbols, lanes, skip)`` of a bit stream: ``(0, 1, False)`` for a raw
+    stock stream, else the sub-stream length and the layout its magic names."""
     if len(string) >= 16 and len(string) % 4 == 0:
         magic, L, S, ns = struct.unpack_from("<4I", string, 0)
-        if magic == MAGIC and L == n_symbols and S > 0 and ns == (L + S - 1) // S and \
-                len(string) >= 4 * (4 + ns):
-            return S
-    return 0
+        if magic in (MAGIC, MAGIC_LANES, MAGIC_LANES_SKIP) and L == n_symbols and S > 0 and \
+                ns == (L + S - 1) // S and len(string) >= 4 * (4 + ns):
+            return S, (1 if magic == MAGIC else 32), magic == MAGIC_LANES_SKIP
+    return 0, 1, False
+
+
+def check_decode_status(statuses):
+    """One device->host read for the status words of any number of decoder
+    launches (``rans_decode(..., statuses=[...])``); raises like ``rans_decode``."""
+    if not statuses:
+        return
+    st = 0
+    for v in torch.cat(statuses).cpu().tolist():
+        st |= int(v)
+    if st != 0:
+        # bit 0: an index outside the tables (wins: the stream then cannot decode either),
+        # bit 1: malformed container
+        raise ValueError("decompress: " + ("an index lies outside the CDF tables" if st & 1
+                                           else "malformed bit-stream container"))
 
 
 def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=None,
-                scale_bound=0.11, means=None, device=None, want_symbols=False, cb=None):
+                scale_bound=0.11, means=None, device=None, want_symbols=False, cb=None,
+                statuses=None):
     """Decode ``len(strings)`` bit streams into a ``[N,C,H,W]`` tensor
     ``float(symbol) + means`` (``EntropyModel.dequantize``), or int32 symbols.
     ``cb = (parity, alt_elements)``: checkerboard pairing of ``scales`` (see
-    ``dvc_rans_decode`` in include/dvc_b200.h)."""
+    ``dvc_rans_decode`` in include/dvc_b200.h).  ``statuses``: a list that
+    receives this launch's status word instead of a host synchronisation here;
+    the caller hands the list to ``check_decode_status`` once everything that
+    depends on the decoded values is queued (the context models do: one read per
+    ``decompress`` instead of three stalls)."""
     if not isinstance(strings, (tuple, list)):
         raise ValueError("Invalid `strings` parameter type.")
     n, c, h, w = (int(v) for v in shape)
@@ -335,10 +450,12 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
         raise ValueError("Invalid strings or indexes parameters")
     dev = tables.cdf.device if device is None else device
     L = c * h * w
-    S = {stream_symbols_of(s, L) for s in strings}
+    S = {container_of(s, L) for s in strings}
     if len(S) != 1:
         raise ValueError("bit streams of one batch were written with different layouts")
-    S = S.pop()
+    S, lanes, skip = S.pop()
+    marks = tables.skip_rows() if skip else None
+    lut = tables.cdf_lut() if lanes == 32 else None
     for s in strings:
         if len(s) < 8 or len(s) % 4:
             raise ValueError("truncated bit stream")
@@ -357,6 +474,12 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
     else:
         out_f = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
     status = _status_word(dev)
+    scratch = None
+    if lanes == 32:
+        nbytes = nat.lib().dvc_rans_decode_scratch_bytes(n, L, int(S), lanes)
+        if nbytes < 0:
+            raise nat.DvcError(f"rans_decode: unsupported partition (L={L}, S={S})")
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     with nat.device_of(buf):
         rc = nat.lib().dvc_rans_decode(
             buf.data_ptr(), stride, in_bytes.data_ptr(), ip, sp, tp, T, float(scale_bound),
@@ -364,12 +487,13 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
             tables.cdf.size(0), tables.cdf.size(1), nat.ptr(means), nat.ptr(out_f),
             nat.ptr(out_s), status.data_ptr(), n, c, h, w, sst, nat.opt_st4(means),
             nat.opt_st4(out_f), int(S), -1 if cb is None else int(cb[0]),
-            0 if cb is None else int(cb[1]), nat.stream_of(buf))
+            0 if cb is None else int(cb[1]), lanes, nat.ptr(marks), nat.ptr(lut),
+            nat.ptr(scratch), nat.stream_of(buf))
     nat.check(rc, "dvc_rans_decode")
-    st = int(status.item())
-    if st != 0:
-        raise ValueError("decompress: " + ("an index lies outside the CDF tables" if st == 1
-                                           else "malformed bit-stream container"))
+    if statuses is not None:
+        statuses.append(status)
+    else:
+        check_decode_status([status])
     return out_s if want_symbols else out_f
 
 

@@ -325,17 +325,17 @@ def frame_context_compress(self, y, y_ref, context):
     return _compress_tail(self, y, z, z_hat, means_hat, scales_hat, z_pending)
 
 
-def _decompress_head(self, strings, shape):
+def _decompress_head(self, strings, shape, statuses):
     from . import coder
     assert isinstance(strings, list) and len(strings) == 3
     eb = self.entropy_bottleneck
     tables = _coder_tables(eb)
     out_shape = (len(strings[2]), tables.cdf.size(0), int(shape[0]), int(shape[1]))
     return coder.rans_decode(strings[2], tables, out_shape, means=_medians(eb),
-                             device=tables.cdf.device)
+                             device=tables.cdf.device, statuses=statuses)
 
 
-def _decompress_tail(self, strings, means_hat, scales_hat):
+def _decompress_tail(self, strings, means_hat, scales_hat, statuses):
     """Two decoding passes around the spatial prior (video_model.py:259-289):
     the checkerboard scale planes are read in place by the decoder (no masks, no
     build_indexes tensor), symbols stay int32 on the device, and two
@@ -349,29 +349,36 @@ def _decompress_tail(self, strings, means_hat, scales_hat):
     half = c // 2
     q0 = coder.rans_decode(strings[0], tables, (n, half, h, w), scales=scales_hat[:, :half],
                            scale_table=gc.scale_table, scale_bound=sb, want_symbols=True,
-                           cb=(0, half * scales_hat.stride(1)), device=means_hat.device)
+                           cb=(0, half * scales_hat.stride(1)), device=means_hat.device,
+                           statuses=statuses)
     params = coder.decode_stage_a(q0, means_hat, scales_hat)
     prior = self.y_spatial_prior(params)
     q1 = coder.rans_decode(strings[1], tables, (n, half, h, w), scales=prior[:, half:c],
                            scale_table=gc.scale_table, scale_bound=sb, want_symbols=True,
-                           cb=(1, c * prior.stride(1)), device=means_hat.device)
-    return coder.decode_stage_b(q0, q1, means_hat, prior)
+                           cb=(1, c * prior.stride(1)), device=means_hat.device,
+                           statuses=statuses)
+    y_hat = coder.decode_stage_b(q0, q1, means_hat, prior)
+    # the three decoder launches and everything between them are queued: ONE host read
+    coder.check_decode_status(statuses)
+    return y_hat
 
 
 def motion_context_decompress(self, strings, shape, y_ref):
     """Drop-in for ``MotionContextModel.decompress`` (video_model.py:255-291)."""
-    z_hat = _decompress_head(self, strings, shape)
+    statuses = []
+    z_hat = _decompress_head(self, strings, shape, statuses)
     n, _, h, w = z_hat.shape
     params = self.hyper_decoder(z_hat)
     if y_ref is None:
         y_ref = torch.zeros([n, params.size(1) // 2, h * 4, w * 4], device=z_hat.device)
     means_hat, scales_hat = self.y_prior_fusion(torch.cat((params, y_ref), dim=1)).chunk(2, 1)
-    return _decompress_tail(self, strings, means_hat, scales_hat)
+    return _decompress_tail(self, strings, means_hat, scales_hat, statuses)
 
 
 def frame_context_decompress(self, strings, shape, y_ref, context):
     """Drop-in for ``FrameContextModel.decompress`` (video_model.py:429-466)."""
-    z_hat = _decompress_head(self, strings, shape)
+    statuses = []
+    z_hat = _decompress_head(self, strings, shape, statuses)
     n, _, h, w = z_hat.shape
     params = self.hyper_decoder(z_hat)
     if y_ref is None:
@@ -379,4 +386,4 @@ def frame_context_decompress(self, strings, shape, y_ref, context):
     temporal_params = self.temporal_prior_encoder(context)
     means_hat, scales_hat = self.y_prior_fusion(
         torch.cat((temporal_params, params, y_ref), dim=1)).chunk(2, 1)
-    return _decompress_tail(self, strings, means_hat, scales_hat)
+    return _decompress_tail(self, strings, means_hat, scales_hat, statuses)

@@ -94,10 +94,11 @@ __device__ __forceinline__ int scale_index(float s, float bound, const float* ta
 }
 
 __device__ __forceinline__ void split_chw(const Source& s, long long e, int& c, int& h, int& w) {
-  c = (int)(e / s.HW);
-  const int r = (int)(e - (long long)c * s.HW);
-  h = r / s.W;
-  w = r - h * s.W;
+  const unsigned ue = (unsigned)e;   // L < 2^31 (fill_source): 32-bit divisions
+  c = (int)(ue / (unsigned)s.HW);
+  const unsigned r = ue - (unsigned)c * (unsigned)s.HW;
+  h = (int)(r / (unsigned)s.W);
+  w = (int)(r - (unsigned)h * (unsigned)s.W);
 }
 
 __device__ __forceinline__ int fetch_symbol(const Source& s, int n, long long e, int c, int h,
@@ -148,6 +149,9 @@ __global__ void __launch_bounds__(256) symbols_indexes_kernel(const SymIdxP p) {
 // ---------------------------------------------------------------------------
 // f2: encoder
 // ---------------------------------------------------------------------------
+struct IlvEncChunk;
+struct IlvDecChunk;
+
 struct EncRec {                 // per-warp shared staging, structure of arrays
   unsigned long long rcp[kChunk];
   uint32_t bias[kChunk];        // start (+ 2^16 - 1 when freq == 1)
@@ -158,6 +162,9 @@ struct EncRec {                 // per-warp shared staging, structure of arrays
 struct EncP {
   Source src;
   Tables tb;
+  const uint8_t* skip;          // [opt] lane-interleaved layout: byte per table row, != 0: value 0 implied
+  const IlvEncChunk* ilv_enc;   // lane-interleaved layout: coder records of every chunk (prepare kernel)
+  int chunks_per_sample;
   uint32_t* stream_words;       // scratch: [N][n_streams]
   uint32_t* stream_data;        // scratch: [N][n_streams][cap]
   long long S;                  // symbols per sub-stream
@@ -289,7 +296,8 @@ struct PackP {
   long long out_stride;   // bytes between samples
   long long* out_bytes;   // [N]: container size, or -(needed) if out_stride is too small
   long long L, S;
-  int n_streams, cap, header;  // header = 1: DVC1 container, 0: raw stock stream
+  int n_streams, cap, header;  // header = 1: container, 0: raw stock stream
+  uint32_t magic;
 };
 
 __global__ void __launch_bounds__(128) rans_pack_kernel(const PackP p) {
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(128) rans_pack_kernel(const PackP p) {
   const uint32_t mine = cnt[j];
   if (p.header) {
     if (j == 0 && threadIdx.x < 4) {
-      const uint32_t hdr[4] = {kMagic, (uint32_t)p.L, (uint32_t)p.S, (uint32_t)p.n_streams};
+      const uint32_t hdr[4] = {p.magic, (uint32_t)p.L, (uint32_t)p.S, (uint32_t)p.n_streams};
       dst[threadIdx.x] = hdr[threadIdx.x];
     }
     if (threadIdx.x == 0) dst[4 + j] = mine;
@@ -346,6 +354,12 @@ struct DecStage {
 struct DecP {
   Source src;                 // indexes / scales / means (symbols, x unused)
   Tables tb;
+  const uint8_t* skip;        // [opt] lane-interleaved layout ('DVS3'): byte per table row
+  const uint16_t* lut;        // [opt] lane-interleaved layout: inverse look-up [n_cdf][65]
+  const IlvDecChunk* ilv_dec; // lane-interleaved layout: pass-1 items of every chunk (prepare kernel)
+  const uint16_t* ilv_ci;     //   table row of every position
+  int32_t* ilv_sym;           //   decoded symbols [N][L]
+  int chunks_per_sample;
   const uint8_t* in;
   long long in_stride;        // bytes between samples
   const long long* in_bytes;  // [N] device
@@ -516,6 +530,680 @@ __global__ void __launch_bounds__(kCoderWarps * 32) rans_decode_kernel(const Dec
 }
 
 // ---------------------------------------------------------------------------
+// f2, lane-interleaved container ('DVC3' / 'DVS3').
+//
+// A GPU lane walks a range-coder chain ~10x slower than a CPU core, and every
+// independent chain costs its flush bytes, so the 'DVC1' layout (one chain per
+// warp, 12 bytes per chain) has to choose between bytes and time.  Here a
+// sub-stream is coded by the 32 lanes of ONE warp, each lane a stock rans64
+// state (same per-symbol arithmetic as above, bypass coding included); item k
+// of the sub-stream's item list belongs to lane k % 32 and is coded in round
+// k / 32.  The lanes share one word stream: in every step the lanes that
+// renormalise take consecutive words in lane order (ballot + popc), so the
+// words of a round are contiguous and the decoder reads them with the same
+// ballot.  A step is the t-th rans operation of a lane's item (t = 0: the
+// symbol, t = 1: bypass count nibble, t >= 2: bypass data nibbles).  Flush: a
+// mask word (bit l: lane l's state needs a high word), then the 32 states,
+// 1 or 2 words each -- 132..260 bytes per sub-stream for 32 chains, i.e.
+// 4..8 bytes per chain instead of 12.
+//
+// 'DVS3' adds implied zeros.  At low rates most latents of a DMC-style codec sit
+// in the narrowest table rows (sigma at the 0.11 floor), where value 0 holds
+// >= 65528/65536 of the mass: coding one costs ~1e-4 bit but a full chain step.
+// `skip_rows` marks those rows (one byte per row, derived by both sides from the
+// tables).  Positions are handled in chunks of 1024 = 32 groups of 32; pass 1 of
+// a chunk codes, group by group, the regular symbols and -- for a group that has
+// marked positions -- ONE flag "some marked symbol of this group is not 0"
+// (P(flag) = 8 k / 65536 for k marked positions, an upper bound of what the
+// tables say); pass 2 codes the marked symbols of the flagged groups with their
+// ordinary table rows.  The chain is up to 32x shorter on the marked symbols, the
+// bits are those of the stock coder (a flag costs what its zeros would have cost)
+// plus ~8 bits per flagged group, and nothing is lossy: y_hat is bit-identical.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kMagic3 = 0x33435644u;    // "DVC3"
+constexpr uint32_t kMagic3S = 0x33535644u;   // "DVS3": + implied-zero groups
+constexpr int kIlvChunk = 1024;              // positions per chunk (32 groups x 32 lanes)
+constexpr int kIlvItems = kIlvChunk + 32;    // + one flag per group
+constexpr int kRowCache = 256;               // table rows whose size/offset/mark live in shared memory
+constexpr int kLutBuckets = 64;              // inverse-CDF look-up: 64 buckets of 1024 counts per row
+constexpr int kLutStride = kLutBuckets + 1;
+constexpr int kIlvRing = 5;                  // chunks in flight between the copy engine and the chain
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- PTX wrappers: mbarrier + 1-D bulk copy (the copy engine fills the chain's stages) -------
+__device__ __forceinline__ uint32_t ilv_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void ilv_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ilv_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void ilv_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (!ok && ++spins > (1u << 20)) __trap();   // a lost copy traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void ilv_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+struct IlvRows {                   // per CTA, loaded once
+  int2 so[kRowCache];              // (cdf_size, offset) of a table row
+  uint8_t mark[kRowCache];
+  float tab[kMaxTable];
+};
+__device__ __forceinline__ void ilv_load_rows(IlvRows& R, const Source& src, const Tables& tb,
+                                              const uint8_t* skip) {
+  for (int i = threadIdx.x; i < src.T; i += blockDim.x) R.tab[i] = __ldg(src.scale_table + i);
+  for (int i = threadIdx.x; i < min(tb.n_cdf, kRowCache); i += blockDim.x) {
+    R.so[i] = make_int2(__ldg(tb.cdf_size + i), __ldg(tb.offset + i));
+    R.mark[i] = skip ? __ldg(skip + i) : (uint8_t)0;
+  }
+}
+__device__ __forceinline__ int2 ilv_size_off(const IlvRows& R, const Tables& tb, int ci) {
+  return ci < kRowCache ? R.so[ci] : make_int2(__ldg(tb.cdf_size + ci), __ldg(tb.offset + ci));
+}
+__device__ __forceinline__ bool ilv_marked(const IlvRows& R, const uint8_t* skip, int ci) {
+  if (!skip) return false;
+  return (ci < kRowCache ? R.mark[ci] : __ldg(skip + ci)) != 0;
+}
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  total = __shfl_sync(kFull, inc, 31);
+  return inc - v;
+}
+
+// What the data-parallel half (the prepare kernels, one CTA of 1024 threads per chunk, the
+// whole GPU) leaves in global memory for the serial half (the chain kernels, one warp per
+// sub-stream).  Everything is laid out per chunk; sub-streams are whole chunks.
+struct IlvMeta {                   // 16 bytes per chunk
+  int n1, n2;                      // items of pass 1 / pass 2 (decoder: n2 is found while decoding)
+  int flags;                       // bit 0: some item is bypass-coded (encoder), bit 1: marked positions exist
+  int pad;
+};
+struct IlvEncChunk {               // coder records in ITEM order: pass 1 at [0, n1), pass 2 at [n1, n1 + n2)
+  unsigned long long rcp[kIlvItems];   // Rans64EncSymbolInit's exact reciprocal
+  uint32_t bias[kIlvItems];        // start (+ 2^16 - 1 when freq == 1)
+  uint32_t fs[kIlvItems];          // freq | rcp_shift << 17 | operations << 22 (1, or 2 + nibbles)
+  uint32_t raw[kIlvItems];         // bypass payload
+  IlvMeta meta;
+};
+struct IlvDecChunk {               // pass-1 items in order
+  uint4 item[kIlvItems];           // x: row offset in the CDF table (flag: 65536 - 8k), y: cdf_size,
+                                   // z: offset, w: position (flag: kIlvChunk + g) | table row << 16
+  uint32_t skm[32];                // marked positions of each group
+  IlvMeta meta;
+  uint32_t pad[4];
+};
+static_assert(sizeof(IlvEncChunk) % 16 == 0 && sizeof(IlvDecChunk) % 16 == 0, "bulk-copy granularity");
+
+struct IlvPrepP {
+  Source src;
+  Tables tb;
+  const uint8_t* skip;
+  IlvEncChunk* enc;                // encoder: [N * chunks_per_sample]
+  IlvDecChunk* dec;                // decoder
+  uint16_t* pos_ci;                // decoder: table row of every position [N][chunks_per_sample * 1024]
+  int chunks_per_sample;
+  int* status;
+};
+
+// ---- prepare: one chunk per CTA, warp g = group g, lane = position in the group ---------------
+template <bool kEncoder>
+__global__ void __launch_bounds__(kIlvChunk) ilv_prepare_kernel(const IlvPrepP p) {
+  __shared__ IlvRows R;
+  __shared__ int cnt1[32], cnt2[32];
+  __shared__ int any_esc, any_mark;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int n = blockIdx.x / p.chunks_per_sample;
+  const int c = blockIdx.x - n * p.chunks_per_sample;
+  if (threadIdx.x == 0) { any_esc = 0; any_mark = 0; }
+  ilv_load_rows(R, p.src, p.tb, p.skip);
+  __syncthreads();
+  const long long e = (long long)c * kIlvChunk + threadIdx.x;
+  const bool valid = e < p.src.L;
+  bool sk = false, bad = false;
+  int sym = 0, ci = 0, ch = 0, h = 0, w = 0;
+  if (valid) {
+    split_chw(p.src, e, ch, h, w);
+    if (kEncoder) sym = fetch_symbol(p.src, n, e, ch, h, w);
+    ci = fetch_index(p.src, n, e, ch, h, w, R.tab);
+    if (ci < 0 || ci >= p.tb.n_cdf) { bad = true; ci = 0; }
+    sk = ilv_marked(R, p.skip, ci);
+  }
+  const uint32_t m_sk = __ballot_sync(kFull, sk);
+  const uint32_t m_rg = __ballot_sync(kFull, valid && !sk);
+  const bool fl = kEncoder && __ballot_sync(kFull, sk && sym != 0) != 0u;
+  if (lane == 0) {
+    cnt1[g] = __popc(m_rg) + (m_sk != 0u ? 1 : 0);
+    cnt2[g] = fl ? __popc(m_sk) : 0;
+    if (m_sk) any_mark = 1;
+  }
+  __syncthreads();
+  int n1, n2;
+  const int s1 = __shfl_sync(kFull, warp_excl_scan(cnt1[lane], lane, n1), g);
+  const int s2 = __shfl_sync(kFull, warp_excl_scan(cnt2[lane], lane, n2), g);
+  const unsigned lt = (1u << lane) - 1u;
+  // slot of this position in the item order (-1: an implied zero, not coded)
+  int slot = -1;
+  if (valid && !sk) slot = s1 + __popc(m_rg & lt);
+  else if (valid && fl) slot = n1 + s2 + __popc(m_sk & lt);
+  const int flag_slot = s1 + __popc(m_rg);       // of the group's flag, when it has one
+  const int2 so = ilv_size_off(R, p.tb, ci);
+  if (kEncoder) {
+    IlvEncChunk& O = p.enc[blockIdx.x];
+    auto put = [&](int at, uint32_t start, uint32_t freq, uint32_t nops, uint32_t raw) {
+      unsigned long long rcp;
+      uint32_t shift, bias;
+      if (freq < 2u) {
+        rcp = ~0ull; shift = 0; bias = start + (1u << 16) - 1u;
+      } else {
+        const uint32_t sh = 32u - (uint32_t)__clz((int)(freq - 1u));  // ceil(log2(freq))
+        const unsigned long long x1 = 1ull << (sh + 31);
+        const unsigned long long t1 = x1 / freq;
+        const unsigned long long x0 = (unsigned long long)(freq - 1u) + ((x1 % freq) << 32);
+        rcp = x0 / freq + (t1 << 32);
+        shift = sh - 1u;
+        bias = start;
+      }
+      O.rcp[at] = rcp; O.bias[at] = bias; O.fs[at] = freq | (shift << 17) | (nops << 22); O.raw[at] = raw;
+    };
+    bool esc = false;
+    if (slot >= 0) {
+      const int32_t* __restrict__ row = p.tb.cdf + (long long)ci * p.tb.cdf_stride;
+      const int max_value = so.x - 2;
+      int value = sym - so.y;
+      uint32_t raw = 0, nops = 1;
+      if (value < 0) {
+        raw = (uint32_t)(-2 * value - 1);
+        value = max_value;
+      } else if (value >= max_value) {
+        raw = (uint32_t)(2 * (value - max_value));
+        value = max_value;
+      }
+      if (max_value < 0) { bad = true; value = 0; }
+      else if (value == max_value) {  // bypass: count nibble + data nibbles
+        uint32_t nb = 0;
+        while (nb < 8 && (raw >> (nb * 4)) != 0) ++nb;
+        nops = 2 + nb;
+        esc = true;
+      }
+      const uint32_t start = (uint32_t)__ldg(row + value);
+      uint32_t freq = (uint32_t)__ldg(row + value + 1) - start;
+      if (freq == 0u || freq > (1u << 16)) { bad = true; freq = 1u; }
+      put(slot, start, freq, nops, raw);
+    }
+    if (lane == 0 && m_sk) {   // the group's flag: P(1) = 8k / 65536
+      const uint32_t f1 = 8u * (uint32_t)__popc(m_sk);
+      put(flag_slot, fl ? (1u << 16) - f1 : 0u, fl ? f1 : (1u << 16) - f1, 1u, 0u);
+    }
+    if (esc) any_esc = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      IlvMeta m;
+      m.n1 = n1; m.n2 = n2; m.flags = (any_esc ? 1 : 0) | (any_mark ? 2 : 0); m.pad = 0;
+      O.meta = m;
+    }
+  } else {
+    IlvDecChunk& O = p.dec[blockIdx.x];
+    if (valid) p.pos_ci[(long long)blockIdx.x * kIlvChunk + threadIdx.x] = (uint16_t)ci;
+    if (slot >= 0)
+      O.item[slot] = make_uint4((uint32_t)((long long)ci * p.tb.cdf_stride), (uint32_t)max(so.x, 2),
+                                (uint32_t)so.y, (uint32_t)threadIdx.x | ((uint32_t)ci << 16));
+    if (lane == 0) {
+      O.skm[g] = m_sk;
+      if (m_sk)
+        O.item[flag_slot] = make_uint4((1u << 16) - 8u * (uint32_t)__popc(m_sk), 3u, 0u,
+                                       (uint32_t)(kIlvChunk + g));
+    }
+    if (threadIdx.x == 0) {
+      IlvMeta m;
+      m.n1 = n1; m.n2 = 0; m.flags = any_mark ? 2 : 0; m.pad = 0;
+      O.meta = m;
+    }
+  }
+  if (bad && p.status) atomicOr(p.status, 1);
+}
+
+// ---- encoder chain ------------------------------------------------------------
+struct IlvEncState {
+  unsigned long long x;
+  uint32_t* reg;     // scratch region of this sub-stream
+  int wpos;          // next free word is reg[wpos - 1] (words grow downwards)
+};
+struct IlvEncRec {
+  unsigned long long rcp;
+  uint32_t bias, fs, raw;
+};
+constexpr uint32_t kIdleFs = 0x1ffffu;   // record of an idle lane: never renormalises, q = 0
+__device__ __forceinline__ IlvEncRec ilv_enc_rec(const IlvEncChunk& T, int base, int k, int n_items) {
+  IlvEncRec r;
+  r.rcp = 0ull; r.bias = 0u; r.fs = kIdleFs; r.raw = 0u;
+  if (k >= 0 && k < n_items) {
+    r.rcp = T.rcp[base + k]; r.bias = T.bias[base + k]; r.fs = T.fs[base + k]; r.raw = T.raw[base + k];
+  }
+  return r;
+}
+
+// One pass of a chunk, rounds last to first; the record of the round after this one is fetched
+// while this one is in the chain.  kBypass = false: no item of the chunk is bypass-coded, a
+// round is one straight-line Rans64EncPut per lane.
+template <bool kBypass>
+__device__ __forceinline__ void ilv_encode_pass(const IlvEncChunk& T, int base, int n_items,
+                                                IlvEncState& E, int lane) {
+  if (n_items <= 0) return;
+  const unsigned gt = lane == 31 ? 0u : (kFull << (lane + 1));
+  int r0 = ((n_items - 1) / 32) * 32;
+  IlvEncRec cur = ilv_enc_rec(T, base, r0 + lane, n_items);
+  for (; r0 >= 0; r0 -= 32) {
+    const IlvEncRec nxt = ilv_enc_rec(T, base, r0 - 32 + lane, n_items);
+    const uint32_t freq = cur.fs & 0x1ffffu, shift = (cur.fs >> 17) & 31u;
+    if (kBypass) {
+      const int nops = (int)(cur.fs >> 22);          // 0 for an idle lane
+      const int tmax = __reduce_max_sync(kFull, nops);
+      for (int t = tmax - 1; t >= 1; --t) {          // Rans64EncPutBits(4): count, data nibbles
+        const bool doing = t < nops;
+        const bool emit = doing && E.x >= (1ull << 59);
+        const unsigned m = __ballot_sync(kFull, emit);
+        if (emit) {
+          E.reg[E.wpos - 1 - __popc(m & gt)] = (uint32_t)E.x;
+          E.x >>= 32;
+        }
+        E.wpos -= __popc(m);
+        if (doing) {
+          const uint32_t v = t == 1 ? (uint32_t)(nops - 2) : (cur.raw >> ((t - 2) * 4)) & 15u;
+          E.x = (E.x << 4) | v;
+        }
+      }
+    }
+    {  // Rans64EncPut: renormalise when x >= freq << 47, then x = (x / freq) << 16 + x % freq + start
+      const bool emit = (uint32_t)(E.x >> 47) >= freq;     // idle lane: freq = 0x1ffff, never
+      const unsigned m = __ballot_sync(kFull, emit);
+      if (emit) {
+        E.reg[E.wpos - 1 - __popc(m & gt)] = (uint32_t)E.x;
+        E.x >>= 32;
+      }
+      E.wpos -= __popc(m);
+      const unsigned long long q = __umul64hi(E.x, cur.rcp) >> shift;   // idle lane: rcp = 0
+      E.x = E.x + cur.bias + q * (unsigned long long)((1u << 16) - freq);
+    }
+    cur = nxt;
+  }
+}
+
+struct IlvEncShared {
+  IlvEncChunk stage[kIlvRing];
+  unsigned long long bar[kIlvRing];
+};
+
+// One warp per sub-stream.  Lane 0 keeps kIlvRing - 1 chunk copies in flight; the warp does
+// nothing but walk the chains.
+__global__ void __launch_bounds__(32) rans_ilv_encode_kernel(const EncP p) {
+  extern __shared__ __align__(128) unsigned char ilv_smem[];
+  IlvEncShared& S = *reinterpret_cast<IlvEncShared*>(ilv_smem);
+  const int lane = threadIdx.x;
+  const int j = blockIdx.x, n = blockIdx.y;
+  const long long s_begin = (long long)j * p.S;
+  const long long s_end = min(p.src.L, s_begin + p.S);
+  const int n_chunks = (int)((s_end - s_begin + kIlvChunk - 1) / kIlvChunk);
+  // chunks last to first
+  const IlvEncChunk* last = p.ilv_enc + (long long)n * p.chunks_per_sample + s_begin / kIlvChunk +
+                            (n_chunks - 1);
+  if (lane == 0) {
+    for (int s = 0; s < kIlvRing; ++s) ilv_mbar_init(ilv_smem_u32(&S.bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < min(kIlvRing - 1, n_chunks); ++i) {
+      ilv_mbar_expect_tx(ilv_smem_u32(&S.bar[i]), (uint32_t)sizeof(IlvEncChunk));
+      ilv_bulk_g2s(ilv_smem_u32(&S.stage[i]), last - i, (uint32_t)sizeof(IlvEncChunk),
+                   ilv_smem_u32(&S.bar[i]));
+    }
+  }
+  __syncwarp();
+  IlvEncState E;
+  E.x = 1ull << 31;  // Rans64EncInit, every lane
+  E.reg = p.stream_data + ((long long)n * p.n_streams + j) * p.cap;
+  E.wpos = p.cap;
+#ifdef DVC_ILV_PROF
+  long long pf_wait = 0, pf_pass = 0, pf_t0 = clock64(), pf_a, pf_b;
+#define PF(acc) pf_b = clock64(); acc += pf_b - pf_a; pf_a = pf_b;
+#else
+#define PF(acc)
+#endif
+  for (int i = 0; i < n_chunks; ++i) {
+    const int s = i % kIlvRing;
+#ifdef DVC_ILV_PROF
+    pf_a = clock64();
+#endif
+    __syncwarp();   // every lane is through with the stage that is refilled now
+    if (lane == 0 && i + kIlvRing - 1 < n_chunks) {
+      const int f = (i + kIlvRing - 1) % kIlvRing;
+      ilv_mbar_expect_tx(ilv_smem_u32(&S.bar[f]), (uint32_t)sizeof(IlvEncChunk));
+      ilv_bulk_g2s(ilv_smem_u32(&S.stage[f]), last - (i + kIlvRing - 1), (uint32_t)sizeof(IlvEncChunk),
+                   ilv_smem_u32(&S.bar[f]));
+    }
+    ilv_mbar_wait(ilv_smem_u32(&S.bar[s]), (uint32_t)((i / kIlvRing) & 1));
+    const IlvEncChunk& T = S.stage[s];
+    const int n1 = T.meta.n1, n2 = T.meta.n2;
+    PF(pf_wait)
+    // last item first (pass 2 is decoded after pass 1)
+    if (T.meta.flags & 1) {
+      ilv_encode_pass<true>(T, n1, n2, E, lane);
+      ilv_encode_pass<true>(T, 0, n1, E, lane);
+    } else {
+      ilv_encode_pass<false>(T, n1, n2, E, lane);
+      ilv_encode_pass<false>(T, 0, n1, E, lane);
+    }
+    PF(pf_pass)
+  }
+#ifdef DVC_ILV_PROF
+  if (lane == 0 && j == 0 && n == 0)
+    printf("enc chain: chunks %d total %lld wait %lld pass %lld\n", n_chunks, clock64() - pf_t0,
+           pf_wait, pf_pass);
+#endif
+  // ---- flush: mask, then the states (1 or 2 words each), lane 0 first -------------
+  const bool wide = (E.x >> 32) != 0ull;
+  const unsigned mask = __ballot_sync(kFull, wide);
+  const int total = 33 + __popc(mask);
+  const int at = E.wpos - total + 1 + lane + __popc(mask & ((1u << lane) - 1u));
+  E.reg[at] = (uint32_t)E.x;
+  if (wide) E.reg[at + 1] = (uint32_t)(E.x >> 32);
+  if (lane == 0) {
+    E.reg[E.wpos - total] = mask;
+    p.stream_words[(long long)n * p.n_streams + j] = (uint32_t)(p.cap - (E.wpos - total));
+  }
+}
+
+// ---- decoder chain ------------------------------------------------------------
+struct IlvDecShared {
+  IlvDecChunk stage[kIlvRing];
+  unsigned long long bar[kIlvRing];
+  IlvRows rows;                    // pass 2 only
+  int val[kIlvChunk];              // values of a chunk that has marked positions
+  uint4 item2[kIlvChunk];          // pass 2, built from the decoded flags
+  uint32_t flag[32];
+  uint16_t lut[8];                 // [min(n_cdf, kRowCache)][kLutStride] when a LUT is given
+};
+
+struct IlvDecState {
+  unsigned long long x;
+  const uint32_t* wp;   // words of this sub-stream
+  int wn, base;         // their number; next unread word
+  bool malformed;
+  __device__ __forceinline__ uint32_t word(int i) const {
+    return (i < wn) ? __ldg(wp + i) : 0u;   // a corrupt stream reads zeros, never out of bounds
+  }
+};
+
+constexpr uint32_t kIdleItem = 0xffffu;   // position field of an idle lane
+
+// One pass.  `direct`: the chunk has no marked position -- item k is position k and its value
+// goes straight to global memory (coalesced); otherwise values are collected in shared memory.
+template <bool kLut>
+__device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, const uint4* items,
+                                                int n_items, int32_t* direct, IlvDecState& D,
+                                                int lane) {
+  if (n_items <= 0) return;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint4 idle = make_uint4(0u, 2u, 0u, kIdleItem);
+  uint4 cur = lane < n_items ? items[lane] : idle;
+  uint32_t window = D.word(D.base + lane);   // the next 32 words, one per lane
+  for (int r0 = 0; r0 < n_items; r0 += 32) {
+    const uint4 nxt = r0 + 32 + lane < n_items ? items[r0 + 32 + lane] : idle;
+    const uint32_t it = cur.w & 0xffffu;
+    const bool act = it != kIdleItem;
+    const bool isflag = act && it >= (uint32_t)kIlvChunk;
+    const int size = (int)cur.y;
+    const uint32_t cum = (uint32_t)(D.x & 0xffffu);  // Rans64DecGet
+    // s = max j in [0, size-1) with row[j] <= cum  (row[0] = 0, row[size-1] = 2^16).
+    // invariant row[lo] <= cum < row[hi]; next = 0 while row[hi] has not been read
+    int lo = 0;
+    uint32_t start = 0, next = 1u << 16;
+    if (isflag) {          // the row {0, 65536 - 8k, 65536}
+      if (cum >= cur.x) { lo = 1; start = cur.x; }
+      else next = cur.x;
+    } else if (act) {
+      const int32_t* __restrict__ row = p.tb.cdf + cur.x;
+      int hi = size - 1;
+      next = 0u;
+      if (kLut) {
+        // the look-up brackets the symbol: s(cum) in [lut[b], lut[b + 1]] for b = cum >> 10
+        const uint16_t* lut = S.lut + (cur.w >> 16) * kLutStride + (cum >> 10);
+        lo = lut[0];
+        hi = lut[1] + 1;
+        const uint32_t a0 = (uint32_t)__ldg(row + lo), a1 = (uint32_t)__ldg(row + lo + 1);
+        start = a0;
+        if (cum >= a1) { lo += 1; start = a1; }
+        else { hi = lo + 1; next = a1; }
+      }
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t v = (uint32_t)__ldg(row + mid);
+        if (cum >= v) { lo = mid; start = v; }
+        else { hi = mid; next = v; }
+      }
+      if (next == 0u) next = (uint32_t)__ldg(row + hi);
+    }
+    // Rans64DecAdvance
+    if (act) D.x = (unsigned long long)(next - start) * (D.x >> 16) + cum - start;
+    {
+      const bool need = act && D.x < (1ull << 31);
+      const unsigned m = __ballot_sync(kFull, need);
+      const uint32_t wv = __shfl_sync(kFull, window, __popc(m & lt));
+      if (need) D.x = (D.x << 32) | wv;
+      D.base += __popc(m);
+    }
+    // bypass (Rans64DecGetBits(4) chain): one operation per lane and step, lanes in order
+    const bool esc = act && !isflag && lo == size - 2;
+    uint32_t raw = 0;
+    if (__any_sync(kFull, esc)) {
+      int ph = esc ? 1 : 0;  // 1: count nibbles, 2: data nibbles
+      int nb = 0, kk = 0;
+      do {
+        const bool doing = ph != 0;
+        const uint32_t val = (uint32_t)(D.x & 15u);
+        if (doing) D.x >>= 4;
+        const bool need = doing && D.x < (1ull << 31);
+        const unsigned m = __ballot_sync(kFull, need);
+        if (need) D.x = (D.x << 32) | D.word(D.base + __popc(m & lt));
+        D.base += __popc(m);
+        if (ph == 1) {
+          nb += (int)val;
+          if (val != 15u || nb > 64) {   // the encoder never writes more than 8 data nibbles
+            if (nb > 64) { D.malformed = true; nb = 64; }
+            ph = nb > 0 ? 2 : 0;
+          }
+        } else if (ph == 2) {
+          if (kk < 8) raw |= val << (kk * 4);
+          if (++kk == nb) ph = 0;
+        }
+      } while (__any_sync(kFull, ph != 0));
+    }
+    window = D.word(D.base + lane);
+    if (act) {
+      if (isflag) {
+        S.flag[it - kIlvChunk] = (uint32_t)lo;
+      } else {
+        int value = lo;
+        if (esc) {
+          value = (int)(raw >> 1);
+          if (raw & 1u) value = -value - 1;
+          else value += size - 2;
+        }
+        value += (int)cur.z;
+        if (direct) direct[it] = value;
+        else S.val[it] = value;
+      }
+    }
+    cur = nxt;
+  }
+}
+
+template <bool kLut>
+__global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
+  extern __shared__ __align__(128) unsigned char ilv_smem[];
+  IlvDecShared& S = *reinterpret_cast<IlvDecShared*>(ilv_smem);
+  const int lane = threadIdx.x;
+  const int j = blockIdx.x, n = blockIdx.y;
+  const long long s_begin = (long long)j * p.S;
+  const long long s_end = min(p.src.L, s_begin + p.S);
+  const int n_chunks = (int)((s_end - s_begin + kIlvChunk - 1) / kIlvChunk);
+  const long long first_chunk = (long long)n * p.chunks_per_sample + s_begin / kIlvChunk;
+  const IlvDecChunk* first = p.ilv_dec + first_chunk;
+  if (lane == 0) {
+    for (int s = 0; s < kIlvRing; ++s) ilv_mbar_init(ilv_smem_u32(&S.bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < min(kIlvRing - 1, n_chunks); ++i) {
+      ilv_mbar_expect_tx(ilv_smem_u32(&S.bar[i]), (uint32_t)sizeof(IlvDecChunk));
+      ilv_bulk_g2s(ilv_smem_u32(&S.stage[i]), first + i, (uint32_t)sizeof(IlvDecChunk),
+                   ilv_smem_u32(&S.bar[i]));
+    }
+  }
+  ilv_load_rows(S.rows, p.src, p.tb, p.skip);
+  if (kLut)
+    for (int i = lane; i < p.tb.n_cdf * kLutStride; i += 32) S.lut[i] = __ldg(p.lut + i);
+  __syncwarp();
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(p.in + n * p.in_stride);
+  const long long total_words = __ldg(p.in_bytes + n) >> 2;
+  IlvDecState D;
+  D.malformed = false;
+  {
+    bool ok = total_words >= 4 + p.n_streams && __ldg(words) == (p.skip ? kMagic3S : kMagic3) &&
+              __ldg(words + 1) == (uint32_t)p.src.L && __ldg(words + 2) == (uint32_t)p.S &&
+              __ldg(words + 3) == (uint32_t)p.n_streams;
+    unsigned long long before = 0;
+    if (ok)
+      for (int i = lane; i < j; i += 32) before += __ldg(words + 4 + i);
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFull, before, o);
+    const unsigned long long mine = ok ? __ldg(words + 4 + j) : 0ull;
+    const long long first_word = 4 + p.n_streams + (long long)before;
+    if (!ok || mine < 33ull || mine > 0x7fffffffull || first_word + (long long)mine > total_words) {
+      D.malformed = true;
+      D.wp = words;   // decode zeros: defined, flagged
+      D.wn = 0;
+    } else {
+      D.wp = words + first_word;
+      D.wn = (int)mine;
+    }
+  }
+  {  // the 32 states
+    const uint32_t mask = D.word(0);
+    const int at = 1 + lane + __popc(mask & ((1u << lane) - 1u));
+    D.x = (unsigned long long)D.word(at);
+    if ((mask >> lane) & 1u) D.x |= (unsigned long long)D.word(at + 1) << 32;
+    D.base = 33 + __popc(mask);
+  }
+  int32_t* const sym_out = p.ilv_sym + (long long)n * p.src.L;
+#ifdef DVC_ILV_PROF
+  long long pf_wait = 0, pf_pass = 0, pf_t0 = clock64(), pf_a, pf_b;
+#endif
+  for (int i = 0; i < n_chunks; ++i) {
+    const int s = i % kIlvRing;
+#ifdef DVC_ILV_PROF
+    pf_a = clock64();
+#endif
+    __syncwarp();   // every lane is through with the stage that is refilled now
+    if (lane == 0 && i + kIlvRing - 1 < n_chunks) {
+      const int f = (i + kIlvRing - 1) % kIlvRing;
+      ilv_mbar_expect_tx(ilv_smem_u32(&S.bar[f]), (uint32_t)sizeof(IlvDecChunk));
+      ilv_bulk_g2s(ilv_smem_u32(&S.stage[f]), first + (i + kIlvRing - 1), (uint32_t)sizeof(IlvDecChunk),
+                   ilv_smem_u32(&S.bar[f]));
+    }
+    ilv_mbar_wait(ilv_smem_u32(&S.bar[s]), (uint32_t)((i / kIlvRing) & 1));
+    const IlvDecChunk& T = S.stage[s];
+    const long long cb = s_begin + (long long)i * kIlvChunk;
+    const int n_valid = (int)min((long long)kIlvChunk, s_end - cb);
+    const int n1 = T.meta.n1;
+    const bool marks = (T.meta.flags & 2) != 0;
+    PF(pf_wait)
+    if (!marks) {
+      // every position is a pass-1 item in position order
+      ilv_decode_pass<kLut>(p, S, T.item, n1, sym_out + cb, D, lane);
+    } else {
+      for (int k = lane; k < kIlvChunk; k += 32) S.val[k] = 0;   // implied zeros
+      __syncwarp();
+      ilv_decode_pass<kLut>(p, S, T.item, n1, nullptr, D, lane);
+      __syncwarp();
+      // pass 2: the marked symbols of the groups whose flag came out set (lane g <-> group g)
+      const uint32_t skm = T.skm[lane];
+      unsigned fm = __ballot_sync(kFull, skm != 0u && S.flag[lane] != 0u);
+      int n2 = 0;
+      while (fm) {
+        const int g = __ffs((int)fm) - 1;
+        fm &= fm - 1u;
+        const uint32_t sm = __shfl_sync(kFull, skm, g);
+        if ((sm >> lane) & 1u) {
+          const int pos = 32 * g + lane;
+          const int ci = __ldg(p.ilv_ci + (first_chunk + i) * kIlvChunk + pos);
+          const int2 so = ilv_size_off(S.rows, p.tb, ci);
+          S.item2[n2 + __popc(sm & ((1u << lane) - 1u))] =
+              make_uint4((uint32_t)((long long)ci * p.tb.cdf_stride), (uint32_t)max(so.x, 2),
+                         (uint32_t)so.y, (uint32_t)pos | ((uint32_t)ci << 16));
+        }
+        n2 += __popc(sm);
+      }
+      __syncwarp();
+      ilv_decode_pass<kLut>(p, S, S.item2, n2, nullptr, D, lane);
+      __syncwarp();
+      for (int k = lane; k < n_valid; k += 32) sym_out[cb + k] = S.val[k];
+    }
+    PF(pf_pass)
+  }
+#ifdef DVC_ILV_PROF
+  if (lane == 0 && j == 0 && n == 0)
+    printf("dec chain: chunks %d total %lld wait %lld pass %lld\n", n_chunks, clock64() - pf_t0,
+           pf_wait, pf_pass);
+#endif
+  // a well-formed sub-stream ends with every lane back at the encoder's initial state and
+  // every word consumed
+  if (D.x != (1ull << 31) || D.base != D.wn) D.malformed = true;
+  if (p.status && __any_sync(kFull, D.malformed) && lane == 0) atomicOr(p.status, 2);
+}
+
+// float(symbol) + means -> out (EntropyModel.dequantize), data parallel
+struct IlvFinishP {
+  Source src;
+  const int32_t* sym;      // [N][L]
+  float* out_f;
+  CTS os;
+  int N;
+};
+__global__ void __launch_bounds__(256) ilv_finish_kernel(const IlvFinishP p) {
+  const long long total = p.src.L * p.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / p.src.L);
+    const long long e = i - n * p.src.L;
+    int c, h, w;
+    split_chw(p.src, e, c, h, w);
+    float f = (float)__ldg(p.sym + i);
+    if (p.src.means)
+      f = add_rn(f, __ldg(p.src.means + n * p.src.ms.n + c * p.src.ms.c + h * p.src.ms.h +
+                          w * p.src.ms.w));
+    p.out_f[n * p.os.n + c * p.os.c + h * p.os.h + w * p.os.w] = f;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Decoder side of the checkerboard dual prior (video_model.py:259-289 ==
 // :433-464): element-wise glue between the two decoding passes and the
 // spatial-prior conv.  q0 / q1 are the decoded symbol planes [N, C/2, H, W]
@@ -618,15 +1306,21 @@ struct Partition {
   long long S;
   int n_streams, cap, header;
 };
-static int make_partition(Partition& q, long long L, int64_t stream_symbols, const char* who) {
+static int make_partition(Partition& q, long long L, int64_t stream_symbols, int lanes,
+                          const char* who) {
   DVC_REQUIRE(stream_symbols >= 0, "%s: stream_symbols must be >= 0", who);
+  DVC_REQUIRE(lanes == 1 || (lanes == 32 && stream_symbols > 0 && stream_symbols % 1024 == 0),
+              "%s: lanes must be 1, or 32 together with stream_symbols > 0 and a multiple of 1024 "
+              "(a raw stream is a stock stream)", who);
   q.header = stream_symbols > 0 ? 1 : 0;
   q.S = q.header ? stream_symbols : L;
   const long long ns = (L + q.S - 1) / q.S;
   DVC_REQUIRE(ns >= 1 && ns <= (1 << 20), "%s: too many sub-streams (%lld)", who, ns);
   DVC_REQUIRE(2 * q.S + 4 < 2147483647LL, "%s: sub-stream too long", who);
   q.n_streams = (int)ns;
-  q.cap = (int)(2 * q.S + 4);  // <= 52 bits per symbol + initial state + flush
+  // <= 52 bits per symbol + initial state + flush; lane-interleaved: 32 states (<= 65 words
+  // with the mask) and <= 16 bits per group flag (one per 32 symbols)
+  q.cap = lanes == 32 ? (int)(2 * q.S + 160) : (int)(2 * q.S + 4);
   return DVC_OK;
 }
 
@@ -712,15 +1406,29 @@ int dvc_pmf_to_quantized_cdf(const float* pmf, int64_t n, int precision, int32_t
   return DVC_OK;
 }
 
-int64_t dvc_rans_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols) {
+int64_t dvc_rans_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols, int lanes) {
   Partition q;
-  if (N < 1 || L < 1 || make_partition(q, L, stream_symbols, "rans_scratch_bytes")) return -1;
-  return N * (int64_t)q.n_streams * (int64_t)(q.cap + 1) * 4;
+  if (N < 1 || L < 1 || make_partition(q, L, stream_symbols, lanes, "rans_scratch_bytes"))
+    return -1;
+  int64_t bytes = N * (int64_t)q.n_streams * (int64_t)(q.cap + 1) * 4;
+  if (lanes == 32)   // + the coder records of every chunk (prepare kernel -> chain kernel)
+    bytes = ((bytes + 15) / 16) * 16 + N * ((L + kIlvChunk - 1) / kIlvChunk) * (int64_t)sizeof(IlvEncChunk);
+  return bytes;
 }
 
-int64_t dvc_rans_max_bytes(int64_t L, int64_t stream_symbols) {
+int64_t dvc_rans_decode_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols, int lanes) {
   Partition q;
-  if (L < 1 || make_partition(q, L, stream_symbols, "rans_max_bytes")) return -1;
+  if (N < 1 || L < 1 || make_partition(q, L, stream_symbols, lanes, "rans_decode_scratch_bytes"))
+    return -1;
+  if (lanes != 32) return 0;
+  const int64_t chunks = N * ((L + kIlvChunk - 1) / kIlvChunk);
+  // pass-1 items of every chunk, table row of every position, decoded symbols
+  return chunks * (int64_t)sizeof(IlvDecChunk) + chunks * kIlvChunk * 2 + ((N * L * 4 + 15) / 16) * 16;
+}
+
+int64_t dvc_rans_max_bytes(int64_t L, int64_t stream_symbols, int lanes) {
+  Partition q;
+  if (L < 1 || make_partition(q, L, stream_symbols, lanes, "rans_max_bytes")) return -1;
   return ((q.header ? 4 + (int64_t)q.n_streams : 0) + (int64_t)q.n_streams * q.cap) * 4;
 }
 
@@ -731,9 +1439,11 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
                     int64_t out_stride_bytes, int64_t* out_bytes, void* scratch, int* status,
                     int64_t N, int64_t C, int64_t H, int64_t W, const int64_t x_st[4],
                     const int64_t means_st[4], const int64_t scales_st[4],
-                    int64_t stream_symbols, dvc_stream_t stream) {
+                    int64_t stream_symbols, int lanes, const uint8_t* skip_rows,
+                    dvc_stream_t stream) {
   DVC_REQUIRE((x != nullptr) != (symbols != nullptr),
               "rans_encode: give exactly one of x / symbols");
+  DVC_REQUIRE(!skip_rows || lanes == 32, "rans_encode: skip_rows needs the lane-interleaved layout");
   DVC_REQUIRE(out && out_bytes && scratch, "rans_encode: null output / scratch");
   DVC_REQUIRE(N > 0 && N <= 65535, "rans_encode: N must be in [1, 65535]");
   DVC_REQUIRE((out_stride_bytes % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0,
@@ -745,21 +1455,47 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
   rc = fill_tables(p.tb, cdf, cdf_size, offset, n_cdf, cdf_stride, "rans_encode");
   if (rc) return rc;
   Partition q;
-  rc = make_partition(q, p.src.L, stream_symbols, "rans_encode");
+  rc = make_partition(q, p.src.L, stream_symbols, lanes, "rans_encode");
   if (rc) return rc;
+  DVC_REQUIRE(lanes == 1 || n_cdf <= 65535, "rans_encode: more than 65535 table rows");
   p.S = q.S; p.n_streams = q.n_streams; p.cap = q.cap; p.N = (int)N;
   p.stream_words = reinterpret_cast<uint32_t*>(scratch);
   p.stream_data = p.stream_words + N * (int64_t)q.n_streams;
   p.status = status;
-  dim3 grid((unsigned)((q.n_streams + kCoderWarps - 1) / kCoderWarps), (unsigned)N);
-  rans_encode_kernel<<<grid, kCoderWarps * 32, 0, (cudaStream_t)stream>>>(p);
-  rc = check_launch("rans_encode_kernel");
+  p.skip = skip_rows;
+  if (lanes == 32) {
+    DVC_REQUIRE(n_cdf * cdf_stride < 2147483647LL, "rans_encode: CDF table too large");
+    const int64_t cps = (p.src.L + kIlvChunk - 1) / kIlvChunk;
+    const int64_t head = ((N * (int64_t)q.n_streams * (int64_t)(q.cap + 1) * 4 + 15) / 16) * 16;
+    IlvEncChunk* chunks = reinterpret_cast<IlvEncChunk*>(reinterpret_cast<uint8_t*>(scratch) + head);
+    DVC_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15u) == 0, "rans_encode: scratch must be 16-byte aligned");
+    IlvPrepP k;
+    k.src = p.src; k.tb = p.tb; k.skip = skip_rows; k.enc = chunks; k.dec = nullptr; k.pos_ci = nullptr;
+    k.chunks_per_sample = (int)cps; k.status = status;
+    ilv_prepare_kernel<true><<<(unsigned)(N * cps), kIlvChunk, 0, (cudaStream_t)stream>>>(k);
+    rc = check_launch("ilv_prepare_kernel");
+    if (rc) return rc;
+    p.ilv_enc = chunks; p.chunks_per_sample = (int)cps;
+    cudaError_t e = cudaFuncSetAttribute(rans_ilv_encode_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(IlvEncShared));
+    if (e != cudaSuccess)
+      return fail(DVC_ERR_CUDA, "rans_encode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    rans_ilv_encode_kernel<<<dim3((unsigned)q.n_streams, (unsigned)N), 32, sizeof(IlvEncShared),
+                             (cudaStream_t)stream>>>(p);
+    rc = check_launch("rans_ilv_encode_kernel");
+  } else {
+    dim3 grid((unsigned)((q.n_streams + kCoderWarps - 1) / kCoderWarps), (unsigned)N);
+    rans_encode_kernel<<<grid, kCoderWarps * 32, 0, (cudaStream_t)stream>>>(p);
+    rc = check_launch("rans_encode_kernel");
+  }
   if (rc) return rc;
   PackP k;
   k.stream_words = p.stream_words; k.stream_data = p.stream_data;
   k.out = out; k.out_stride = out_stride_bytes;
   k.out_bytes = reinterpret_cast<long long*>(out_bytes);
   k.L = p.src.L; k.S = q.S; k.n_streams = q.n_streams; k.cap = q.cap; k.header = q.header;
+  k.magic = lanes == 32 ? (skip_rows ? kMagic3S : kMagic3) : kMagic;
   rans_pack_kernel<<<dim3((unsigned)q.n_streams, (unsigned)N), 128, 0, (cudaStream_t)stream>>>(k);
   return check_launch("rans_pack_kernel");
 }
@@ -771,8 +1507,10 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
                     float* out, int32_t* out_symbols, int* status, int64_t N, int64_t C,
                     int64_t H, int64_t W, const int64_t scales_st[4], const int64_t means_st[4],
                     const int64_t out_st[4], int64_t stream_symbols, int cb_parity,
-                    int64_t cb_alt, dvc_stream_t stream) {
+                    int64_t cb_alt, int lanes, const uint8_t* skip_rows,
+                    const uint16_t* cdf_lut, void* scratch, dvc_stream_t stream) {
   DVC_REQUIRE(in && in_bytes, "rans_decode: null input");
+  DVC_REQUIRE(!skip_rows || lanes == 32, "rans_decode: skip_rows needs the lane-interleaved layout");
   DVC_REQUIRE(cb_parity < 0 || (cb_parity <= 1 && scales),
               "rans_decode: cb_parity must be -1, or 0/1 together with scales");
   DVC_REQUIRE(out || out_symbols, "rans_decode: nothing to write");
@@ -789,13 +1527,56 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
   rc = fill_tables(p.tb, cdf, cdf_size, offset, n_cdf, cdf_stride, "rans_decode");
   if (rc) return rc;
   Partition q;
-  rc = make_partition(q, p.src.L, stream_symbols, "rans_decode");
+  rc = make_partition(q, p.src.L, stream_symbols, lanes, "rans_decode");
   if (rc) return rc;
+  DVC_REQUIRE(lanes == 1 || n_cdf <= 65535, "rans_decode: more than 65535 table rows");
   p.in = in; p.in_stride = in_stride_bytes;
   p.in_bytes = reinterpret_cast<const long long*>(in_bytes);
   p.out_f = out; p.out_sym = out_symbols; p.os = cts(out_st);
   p.S = q.S; p.n_streams = q.n_streams; p.header = q.header; p.N = (int)N;
   p.status = status;
+  p.skip = skip_rows;
+  p.lut = nullptr;
+  if (lanes == 32) {
+    DVC_REQUIRE(n_cdf * cdf_stride < 2147483647LL, "rans_decode: CDF table too large");
+    DVC_REQUIRE(scratch && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0,
+                "rans_decode: the lane-interleaved layout needs 16-byte aligned scratch "
+                "(dvc_rans_decode_scratch_bytes)");
+    const int64_t cps = (p.src.L + kIlvChunk - 1) / kIlvChunk;
+    uint8_t* sp = reinterpret_cast<uint8_t*>(scratch);
+    IlvDecChunk* chunks = reinterpret_cast<IlvDecChunk*>(sp);
+    sp += N * cps * (int64_t)sizeof(IlvDecChunk);
+    uint16_t* pos_ci = reinterpret_cast<uint16_t*>(sp);
+    sp += N * cps * kIlvChunk * 2;
+    int32_t* syms = reinterpret_cast<int32_t*>(sp);
+    IlvPrepP k;
+    k.src = p.src; k.tb = p.tb; k.skip = skip_rows; k.enc = nullptr; k.dec = chunks; k.pos_ci = pos_ci;
+    k.chunks_per_sample = (int)cps; k.status = status;
+    ilv_prepare_kernel<false><<<(unsigned)(N * cps), kIlvChunk, 0, (cudaStream_t)stream>>>(k);
+    rc = check_launch("ilv_prepare_kernel");
+    if (rc) return rc;
+    p.ilv_dec = chunks; p.ilv_ci = pos_ci; p.chunks_per_sample = (int)cps;
+    p.ilv_sym = out_symbols ? out_symbols : syms;
+    // the look-up is staged in shared memory: only for tables of up to kRowCache rows
+    p.lut = (cdf_lut && n_cdf <= kRowCache) ? cdf_lut : nullptr;
+    const size_t smem = sizeof(IlvDecShared) + (p.lut ? (size_t)n_cdf * kLutStride * 2 : 0);
+    auto kern = p.lut ? rans_ilv_decode_kernel<true> : rans_ilv_decode_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess)
+      return fail(DVC_ERR_CUDA, "rans_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<dim3((unsigned)q.n_streams, (unsigned)N), 32, smem, (cudaStream_t)stream>>>(p);
+    rc = check_launch("rans_ilv_decode_kernel");
+    if (rc || !out) return rc;
+    IlvFinishP f;
+    f.src = p.src; f.sym = p.ilv_sym; f.out_f = out; f.os = p.os; f.N = (int)N;
+    const long long total = p.src.L * N;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    ilv_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(f);
+    return check_launch("ilv_finish_kernel");
+
+  }
   dim3 grid((unsigned)((q.n_streams + kCoderWarps - 1) / kCoderWarps), (unsigned)N);
   rans_decode_kernel<<<grid, kCoderWarps * 32, 0, (cudaStream_t)stream>>>(p);
   return check_launch("rans_decode_kernel");

@@ -363,6 +363,24 @@ int dvc_symbols_indexes_fwd(const float* x, const float* means,
  * S = 0: ONE raw stock stream, no header -- byte-identical to CompressAI's
  * RansEncoder.encode_with_indexes (interop mode; serial, slow).
  *
+ * `lanes` = 32 (S > 0 and a multiple of 1024) selects the lane-interleaved layout, magic 'DVC3':
+ * the 32 lanes of the warp that owns a sub-stream each carry a stock rans64
+ * state (item k of the sub-stream -> lane k % 32, round k / 32; same per-symbol
+ * arithmetic and bypass coding as the stock coder) and share one word stream,
+ * renormalising lanes taking consecutive words in lane order.  Sub-stream:
+ *   mask (bit l: lane l's final state has a high word), the 32 states (1 or 2
+ *   words each, lane 0 first), then the words of rounds 0, 1, ... in decode order.
+ * 32 chains cost 132..260 bytes instead of 32 x 12.  `skip_rows` [opt, lanes =
+ * 32 only; magic 'DVS3']: one device byte per table row, != 0 where value 0
+ * (table position -offset) holds >= 65528/65536 of the row's mass; both sides
+ * derive it from the tables.  Positions are taken in chunks of 1024 = 32 groups
+ * of 32.  Pass 1 of a chunk codes, group by group, the symbols of unmarked rows
+ * and, for a group with k >= 1 marked positions, one flag "a marked symbol of
+ * the group is not 0" with P(1) = 8k/65536; pass 2 codes the marked symbols of
+ * the flagged groups with their own rows.  Unflagged marked symbols are 0 and
+ * take no chain step.  Lossless; both layouts round-trip any int32 symbols.
+ * lanes = 1: the 'DVC1' layout above.
+ *
  * Symbols come from `symbols` (int32, contiguous [N][L]) or from `x` [N,C,H,W]
  * (strided) minus `means` [opt] (strided; 0-strides broadcast, e.g. per-channel
  * medians).  Table indexes come from `indexes` (int32, contiguous [N][L]), or
@@ -374,9 +392,9 @@ int dvc_symbols_indexes_fwd(const float* x, const float* means,
  *   out        device bytes, sample n at out + n*out_stride_bytes
  *   out_bytes  device int64[N]: container size of each sample; NEGATIVE
  *              (-needed) when out_stride_bytes was too small (nothing written)
- *   scratch    dvc_rans_scratch_bytes(N, L, S) bytes
+ *   scratch    dvc_rans_scratch_bytes(N, L, S, lanes) bytes
  *   status     [opt] device int, set to 1 if an index fell outside [0, n_cdf)
- * dvc_rans_max_bytes(L, S) is the worst-case container size of one sample.
+ * dvc_rans_max_bytes(L, S, lanes) is the worst-case container size of one sample.
  * ------------------------------------------------------------------------- */
 /* HOST pointers (setup time, once per model): CompressAI's
  * pmf_to_quantized_cdf as EntropyModel._pmf_to_cdf calls it from
@@ -385,8 +403,12 @@ int dvc_symbols_indexes_fwd(const float* x, const float* means,
  * cdf[n] = 2^precision, strictly increasing. */
 int dvc_pmf_to_quantized_cdf(const float* pmf, int64_t n, int precision,
                              int32_t* cdf);
-int64_t dvc_rans_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols);
-int64_t dvc_rans_max_bytes(int64_t L, int64_t stream_symbols);
+int64_t dvc_rans_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols,
+                               int lanes);
+int64_t dvc_rans_max_bytes(int64_t L, int64_t stream_symbols, int lanes);
+/* scratch the decoder needs (0 for lanes = 1); 16-byte aligned device memory */
+int64_t dvc_rans_decode_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols,
+                                      int lanes);
 int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
                     const int32_t* indexes, const float* scales,
                     const float* scale_table, int64_t T, float scale_bound,
@@ -396,13 +418,19 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
                     void* scratch, int* status, int64_t N, int64_t C, int64_t H,
                     int64_t W, const int64_t x_st[4], const int64_t means_st[4],
                     const int64_t scales_st[4], int64_t stream_symbols,
-                    dvc_stream_t stream);
+                    int lanes, const uint8_t* skip_rows, dvc_stream_t stream);
 /* Inverse.  in: device bytes (sample n at in + n*in_stride_bytes, in_bytes
  * device int64[N] = size of each container).  Writes out [opt] = float(symbol)
  * + means [opt] (EntropyModel.dequantize; strided [N,C,H,W]) and/or
  * out_symbols [opt] int32 contiguous.  status [opt]: 1 bad index, 2 malformed
- * container (header/lengths inconsistent with L, S or in_bytes); a malformed
- * container never reads out of bounds. */
+ * container (header/lengths inconsistent with L, S or in_bytes; lanes = 32
+ * also: a sub-stream that does not end on the encoder's initial states with
+ * every word consumed); a malformed container never reads out of bounds.
+ * `lanes` / `skip_rows` must match the container's magic (the Python face
+ * reads it).  cdf_lut [opt, lanes = 32, n_cdf <= 256]: device uint16
+ * [n_cdf][65], an inverse look-up derived from the tables that brackets the
+ * decoder's CDF search: cdf_lut[r][b] = max j with cdf[r][j] <= 1024 b for
+ * b < 64, cdf_lut[r][64] = cdf_size[r] - 2.  Never changes the result. */
 int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes,
                     const int64_t* in_bytes, const int32_t* indexes,
                     const float* scales, const float* scale_table, int64_t T,
@@ -413,7 +441,8 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes,
                     int64_t C, int64_t H, int64_t W, const int64_t scales_st[4],
                     const int64_t means_st[4], const int64_t out_st[4],
                     int64_t stream_symbols, int cb_parity, int64_t cb_alt,
-                    dvc_stream_t stream);
+                    int lanes, const uint8_t* skip_rows, const uint16_t* cdf_lut,
+                    void* scratch, dvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Decoder side of the checkerboard dual prior: the element-wise glue of

@@ -270,3 +270,286 @@ int64_t dvcref_rans_decode_with_indexes(const uint8_t* enc, int64_t nbytes,
   }
   return (int64_t)(ptr - base) * 4;
 }
+
+/* ------------------------------------------------------------------------ */
+/* The lane-interleaved sub-stream of deepvideocodec_b200/csrc/dvc_coder.cu   */
+/* ('DVC3' / 'DVS3' containers, include/dvc_b200.h), restated sequentially.   */
+/*                                                                            */
+/* This is the repository's OWN layout -- nothing in CompressAI corresponds   */
+/* to it.  Every lane is a stock rans64 coder (the operations above); what is */
+/* restated here is the schedule: which lane codes which item, and in which   */
+/* order the lanes' renormalisation words appear in the shared stream.        */
+/*   positions in chunks of 1024 = 32 groups of 32                            */
+/*   pass 1 of a chunk: per group, the symbols of unmarked rows, then (if the */
+/*     group has k >= 1 marked positions) the flag "a marked symbol != 0",    */
+/*     coded as start/freq = (0, 65536-8k) or (65536-8k, 8k)                  */
+/*   pass 2: the marked symbols of the flagged groups                         */
+/*   item i of a pass -> lane i % 32, round i / 32                            */
+/*   step t of a round = the t-th rans operation of every lane that has one,  */
+/*     lanes ascending; decode order = chunks, pass 1, pass 2, rounds, steps  */
+/*   stream = mask, 32 states (1 or 2 words; bit l of mask: 2), round words   */
+/* ------------------------------------------------------------------------ */
+#define ILV_LANES 32
+#define ILV_CHUNK 1024
+
+typedef struct {
+  int32_t lane;
+  sym_t op;
+} lane_op_t;
+
+typedef struct {
+  lane_op_t* v;
+  int64_t n, cap;
+} opvec_t;
+
+static void opvec_push(opvec_t* q, int32_t lane, sym_t op) {
+  if (q->n == q->cap) {
+    q->cap = q->cap ? 2 * q->cap : 1024;
+    q->v = (lane_op_t*)realloc(q->v, sizeof(lane_op_t) * (size_t)q->cap);
+  }
+  q->v[q->n].lane = lane;
+  q->v[q->n].op = op;
+  q->n += 1;
+}
+
+/* the operations of one pass, appended in decode order.  items: position within the chunk, or
+ * -(g + 1) for the flag of group g */
+static void ilv_schedule_pass(opvec_t* q, const int32_t* items, int64_t n_items,
+                              const int32_t* sym, const int32_t* idx, const int32_t* marked_in_group,
+                              const uint8_t* flagged, const int32_t* cdfs, int64_t cdf_stride,
+                              const int32_t* cdf_sizes, const int32_t* offsets) {
+  sym_t ops[ILV_LANES][24];
+  int64_t nops[ILV_LANES];
+  for (int64_t r0 = 0; r0 < n_items; r0 += ILV_LANES) {
+    const int64_t cnt = n_items - r0 < ILV_LANES ? n_items - r0 : ILV_LANES;
+    int64_t tmax = 0;
+    for (int64_t l = 0; l < cnt; ++l) {
+      const int32_t it = items[r0 + l];
+      if (it < 0) {
+        const int32_t g = -it - 1;
+        const uint32_t f1 = 8u * (uint32_t)marked_in_group[g];
+        ops[l][0].bypass = 0;
+        ops[l][0].start = (uint16_t)(flagged[g] ? 65536u - f1 : 0u);
+        /* range can be 65536 - 8k < 65536: fits 16 bits because k >= 1 */
+        ops[l][0].range = (uint16_t)(flagged[g] ? f1 : 65536u - f1);
+        nops[l] = 1;
+      } else {
+        nops[l] = expand(sym[it], idx[it], cdfs, cdf_stride, cdf_sizes, offsets, ops[l]);
+      }
+      if (nops[l] > tmax) tmax = nops[l];
+    }
+    for (int64_t t = 0; t < tmax; ++t)
+      for (int64_t l = 0; l < cnt; ++l)
+        if (t < nops[l]) opvec_push(q, (int32_t)l, ops[l][t]);
+  }
+}
+
+/* group analysis of one chunk; returns the number of pass-1 items */
+static int64_t ilv_lists(const int32_t* idx, int64_t n_valid, const uint8_t* marks,
+                         int32_t* marked_in_group, int32_t* items1) {
+  int64_t n1 = 0;
+  for (int32_t g = 0; g < ILV_CHUNK / ILV_LANES; ++g) {
+    marked_in_group[g] = 0;
+    for (int32_t l = 0; l < ILV_LANES; ++l) {
+      const int64_t pos = (int64_t)g * ILV_LANES + l;
+      if (pos >= n_valid) break;
+      if (marks && marks[idx[pos]]) marked_in_group[g] += 1;
+      else items1[n1++] = (int32_t)pos;
+    }
+    if (marked_in_group[g]) items1[n1++] = -(g + 1);
+  }
+  return n1;
+}
+
+/* Encodes symbols[0..n) into out[0..n_words); returns n_words, -1 if out_cap_words is too
+ * small, -2 on a bad index. */
+int64_t dvcref_ilv_encode(const int32_t* symbols, const int32_t* indexes, int64_t n,
+                          const int32_t* cdfs, int64_t cdf_stride, const int32_t* cdf_sizes,
+                          const int32_t* offsets, int32_t n_cdfs, const uint8_t* marks,
+                          uint32_t* out, int64_t out_cap_words) {
+  for (int64_t i = 0; i < n; ++i)
+    if (indexes[i] < 0 || indexes[i] >= n_cdfs) return -2;
+  opvec_t q = {NULL, 0, 0};
+  int32_t items1[ILV_CHUNK + ILV_LANES], items2[ILV_CHUNK], marked[ILV_CHUNK / ILV_LANES];
+  uint8_t flagged[ILV_CHUNK / ILV_LANES];
+  for (int64_t cb = 0; cb < n; cb += ILV_CHUNK) {
+    const int64_t n_valid = n - cb < ILV_CHUNK ? n - cb : ILV_CHUNK;
+    const int32_t* sym = symbols + cb;
+    const int32_t* idx = indexes + cb;
+    const int64_t n1 = ilv_lists(idx, n_valid, marks, marked, items1);
+    int64_t n2 = 0;
+    for (int32_t g = 0; g < ILV_CHUNK / ILV_LANES; ++g) {
+      flagged[g] = 0;
+      if (!marked[g]) continue;
+      for (int32_t l = 0; l < ILV_LANES && (int64_t)g * ILV_LANES + l < n_valid; ++l) {
+        const int64_t pos = (int64_t)g * ILV_LANES + l;
+        if (marks[idx[pos]] && sym[pos] != 0) flagged[g] = 1;
+      }
+      if (flagged[g])
+        for (int32_t l = 0; l < ILV_LANES && (int64_t)g * ILV_LANES + l < n_valid; ++l) {
+          const int64_t pos = (int64_t)g * ILV_LANES + l;
+          if (marks[idx[pos]]) items2[n2++] = (int32_t)pos;
+        }
+    }
+    ilv_schedule_pass(&q, items1, n1, sym, idx, marked, flagged, cdfs, cdf_stride, cdf_sizes, offsets);
+    ilv_schedule_pass(&q, items2, n2, sym, idx, marked, flagged, cdfs, cdf_stride, cdf_sizes, offsets);
+  }
+  /* the coders run backwards over the schedule; words are written downwards */
+  const int64_t n_words = q.n + 2 * ILV_LANES + 1;
+  uint32_t* buf = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_words);
+  uint32_t* ptr = buf + n_words;
+  uint64_t x[ILV_LANES];
+  for (int l = 0; l < ILV_LANES; ++l) x[l] = RANS64_L;
+  for (int64_t i = q.n - 1; i >= 0; --i) {
+    const sym_t s = q.v[i].op;
+    uint64_t* r = &x[q.v[i].lane];
+    if (!s.bypass) {
+      /* range == 0 encodes 65536 in 16 bits only for a flag with k = 0, which never exists */
+      enc_put(r, &ptr, s.start, s.range, PRECISION);
+    } else {
+      enc_put_bits(r, &ptr, s.start, BYPASS_PRECISION);
+    }
+  }
+  uint32_t mask = 0;
+  for (int l = ILV_LANES - 1; l >= 0; --l) {
+    if (x[l] >> 32) {
+      mask |= 1u << l;
+      *--ptr = (uint32_t)(x[l] >> 32);
+    }
+    *--ptr = (uint32_t)x[l];
+  }
+  *--ptr = mask;
+  const int64_t used = (buf + n_words) - ptr;
+  int64_t rc = used;
+  if (used > out_cap_words) rc = -1;
+  else memcpy(out, ptr, sizeof(uint32_t) * (size_t)used);
+  free(buf);
+  free(q.v);
+  return rc;
+}
+
+typedef struct {
+  const uint32_t* w;
+  int64_t n, at;
+  int overrun;
+} wreader_t;
+
+static uint32_t wr_next(wreader_t* r) {
+  if (r->at >= r->n) {
+    r->overrun = 1;
+    r->at += 1;
+    return 0;
+  }
+  return r->w[r->at++];
+}
+
+/* one pass of the decoder: lanes step in lock step, words taken in lane order */
+static void ilv_decode_pass(wreader_t* rd, uint64_t* x, const int32_t* items, int64_t n_items,
+                            const int32_t* idx, const int32_t* marked_in_group, uint8_t* flagged,
+                            int32_t* val, const int32_t* cdfs, int64_t cdf_stride,
+                            const int32_t* cdf_sizes, const int32_t* offsets) {
+  for (int64_t r0 = 0; r0 < n_items; r0 += ILV_LANES) {
+    const int64_t cnt = n_items - r0 < ILV_LANES ? n_items - r0 : ILV_LANES;
+    int ph[ILV_LANES] = {0}, nb[ILV_LANES] = {0}, kk[ILV_LANES] = {0};
+    uint32_t raw[ILV_LANES] = {0};
+    int32_t sidx[ILV_LANES] = {0};
+    for (int64_t l = 0; l < cnt; ++l) { /* step 0: the symbol / the flag */
+      const int32_t it = items[r0 + l];
+      const uint32_t cum = (uint32_t)(x[l] & 0xffffu);
+      uint32_t start, freq;
+      if (it < 0) {
+        const uint32_t f0 = 65536u - 8u * (uint32_t)marked_in_group[-it - 1];
+        const int f = cum >= f0;
+        flagged[-it - 1] = (uint8_t)f;
+        start = f ? f0 : 0u;
+        freq = f ? 65536u - f0 : f0;
+      } else {
+        const int32_t ci = idx[it];
+        const int32_t* cdf = cdfs + (int64_t)ci * cdf_stride;
+        int32_t j = 0;
+        while (j < cdf_sizes[ci] && !((uint32_t)cdf[j] > cum)) ++j;
+        sidx[l] = j - 1;
+        start = (uint32_t)cdf[j - 1];
+        freq = (uint32_t)(cdf[j] - cdf[j - 1]);
+        if (sidx[l] == cdf_sizes[ci] - 2) ph[l] = 1;
+      }
+      x[l] = (uint64_t)freq * (x[l] >> PRECISION) + cum - start;
+      if (x[l] < RANS64_L) x[l] = (x[l] << 32) | wr_next(rd);
+    }
+    for (;;) { /* bypass nibbles */
+      int any = 0;
+      for (int64_t l = 0; l < cnt; ++l) {
+        if (!ph[l]) continue;
+        any = 1;
+        const uint32_t v = (uint32_t)(x[l] & MAX_BYPASS_VAL);
+        x[l] >>= BYPASS_PRECISION;
+        if (x[l] < RANS64_L) x[l] = (x[l] << 32) | wr_next(rd);
+        if (ph[l] == 1) {
+          nb[l] += (int)v;
+          if (v != MAX_BYPASS_VAL || nb[l] > 64) {
+            if (nb[l] > 64) { nb[l] = 64; rd->overrun = 1; }
+            ph[l] = nb[l] > 0 ? 2 : 0;
+          }
+        } else {
+          if (kk[l] < 8) raw[l] |= v << (kk[l] * BYPASS_PRECISION);
+          if (++kk[l] == nb[l]) ph[l] = 0;
+        }
+      }
+      if (!any) break;
+    }
+    for (int64_t l = 0; l < cnt; ++l) {
+      const int32_t it = items[r0 + l];
+      if (it < 0) continue;
+      const int32_t ci = idx[it];
+      const int32_t max_value = cdf_sizes[ci] - 2;
+      int32_t value = sidx[l];
+      if (value == max_value) {
+        value = (int32_t)(raw[l] >> 1);
+        if (raw[l] & 1) value = -value - 1;
+        else value += max_value;
+      }
+      val[it] = value + offsets[ci];
+    }
+  }
+}
+
+/* Decodes n symbols; returns the words consumed, -2 on a bad index, -3 if the stream is not a
+ * well-formed sub-stream for these indexes (overrun, words left, lanes not back at 2^31). */
+int64_t dvcref_ilv_decode(const uint32_t* words, int64_t n_words, const int32_t* indexes, int64_t n,
+                          const int32_t* cdfs, int64_t cdf_stride, const int32_t* cdf_sizes,
+                          const int32_t* offsets, int32_t n_cdfs, const uint8_t* marks,
+                          int32_t* out) {
+  for (int64_t i = 0; i < n; ++i)
+    if (indexes[i] < 0 || indexes[i] >= n_cdfs) return -2;
+  wreader_t rd = {words, n_words, 0, 0};
+  const uint32_t mask = wr_next(&rd);
+  uint64_t x[ILV_LANES];
+  for (int l = 0; l < ILV_LANES; ++l) {
+    x[l] = wr_next(&rd);
+    if ((mask >> l) & 1u) x[l] |= (uint64_t)wr_next(&rd) << 32;
+  }
+  int32_t items1[ILV_CHUNK + ILV_LANES], items2[ILV_CHUNK], marked[ILV_CHUNK / ILV_LANES];
+  uint8_t flagged[ILV_CHUNK / ILV_LANES];
+  for (int64_t cb = 0; cb < n; cb += ILV_CHUNK) {
+    const int64_t n_valid = n - cb < ILV_CHUNK ? n - cb : ILV_CHUNK;
+    const int32_t* idx = indexes + cb;
+    int32_t* val = out + cb;
+    const int64_t n1 = ilv_lists(idx, n_valid, marks, marked, items1);
+    memset(flagged, 0, sizeof(flagged));
+    ilv_decode_pass(&rd, x, items1, n1, idx, marked, flagged, val, cdfs, cdf_stride, cdf_sizes, offsets);
+    int64_t n2 = 0;
+    for (int32_t g = 0; g < ILV_CHUNK / ILV_LANES; ++g) {
+      if (!marked[g]) continue;
+      for (int32_t l = 0; l < ILV_LANES && (int64_t)g * ILV_LANES + l < n_valid; ++l) {
+        const int64_t pos = (int64_t)g * ILV_LANES + l;
+        if (!marks[idx[pos]]) continue;
+        if (flagged[g]) items2[n2++] = (int32_t)pos;
+        else val[pos] = 0;
+      }
+    }
+    ilv_decode_pass(&rd, x, items2, n2, idx, marked, flagged, val, cdfs, cdf_stride, cdf_sizes, offsets);
+  }
+  int ok = !rd.overrun && rd.at == n_words;
+  for (int l = 0; l < ILV_LANES; ++l) ok = ok && x[l] == RANS64_L;
+  return ok ? rd.at : -3;
+}

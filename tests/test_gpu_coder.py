@@ -148,7 +148,8 @@ def test_container_substreams_are_stock_streams(cuda_dev, gc_pair, shape, S):
     L = shape[1] * shape[2] * shape[3]
     # indexes derived from the scales inside the coder (fused build_indexes)
     strings = coder.rans_encode(p._tables(), x=y, means=means, scales=scales,
-                                scale_table=p.scale_table, scale_bound=0.11, stream_symbols=S)
+                                scale_table=p.scale_table, scale_bound=0.11, stream_symbols=S,
+                                lanes=1)
     idx = o.build_indexes(scales.cpu()).numpy().reshape(shape[0], -1)
     sym = torch.round(y - means).int().cpu().numpy().reshape(shape[0], -1)
     cdf, size, off = _oracle_tables(o)
@@ -182,8 +183,14 @@ def test_module_compress_decompress_match_oracle_modules(cuda_dev, gc_pair, eb_p
                        o.decompress(want, idx_cpu, means=means.cpu()))
     assert torch.equal(p.decompress(o.compress(q.cpu(), idx_cpu), idx).cpu(), q.cpu())
     monkeypatch.setattr(coder, "DEFAULT_STREAM_SYMBOLS", 512)
+    monkeypatch.setattr(coder, "DEFAULT_LANES", 1)
     s = p.compress(y, idx, means)
-    assert s != want and coder.stream_symbols_of(s[0], 8 * 12 * 16) == 512
+    assert s != want and coder.container_of(s[0], 8 * 12 * 16) == (512, 1, False)
+    assert torch.equal(p.decompress(s, idx, means=means), torch.round(y - means) + means)
+    # the default layout: 32 lane-interleaved coders per sub-stream, implied zeros on
+    monkeypatch.setattr(coder, "DEFAULT_LANES", 32)
+    s = p.compress(y, idx, means)
+    assert coder.container_of(s[0], 8 * 12 * 16) == (coder.LANES_STREAM_SYMBOLS, 32, True)
     assert torch.equal(p.decompress(s, idx, means=means), torch.round(y - means) + means)
 
     eo, ep = eb_pair
@@ -274,7 +281,8 @@ def test_full_size_round_trip_and_rate(cuda_dev, gc_pair, c):
     _, lik = p(y, scales, means)
     est_bits = float(-torch.log2(lik.double()).sum())
     for S in (256, 1024, 4096):
-        s = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=S)
+        s = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=S,
+                              lanes=1)
         back = coder.rans_decode(s, p._tables(), shape, indexes=idx, means=means)
         assert torch.equal(back, torch.round(y - means) + means)
         n_streams = -(-c * 68 * 120 // S)
@@ -282,6 +290,17 @@ def test_full_size_round_trip_and_rate(cuda_dev, gc_pair, c):
         overhead = 32 * (4 + n_streams) + 48 * n_streams      # header + ~one state flush each
         # 16-bit tables on a 64-entry scale grid: within a few percent of the estimate
         assert abs(real_bits - overhead - est_bits) < 0.04 * est_bits + 20 * n_streams, \
+            (S, real_bits, est_bits)
+    # lane-interleaved: <= 65 flush words + the length word per sub-stream of 32 chains
+    for S, skip in ((8192, False), (65536, True)):
+        s = coder.rans_encode(p._tables(), x=y, means=means, indexes=idx, stream_symbols=S,
+                              lanes=32, skip=skip)
+        back = coder.rans_decode(s, p._tables(), shape, indexes=idx, means=means)
+        assert torch.equal(back, torch.round(y - means) + means)
+        n_streams = -(-c * 68 * 120 // S)
+        real_bits = 8 * len(s[0])
+        assert coder.container_of(s[0], c * 68 * 120) == (S, 32, skip)
+        assert abs(real_bits - est_bits) < 0.04 * est_bits + 32 * (4 + 66 * n_streams), \
             (S, real_bits, est_bits)
 
 
@@ -362,9 +381,9 @@ def test_payload_driven_substreams(cuda_dev, gc_pair):
         x = torch.round(torch.randn(shape, generator=g).to(cuda_dev) * scales)
         kw = dict(x=x, scales=scales, scale_table=p.scale_table, scale_bound=0.11)
         raw = coder.rans_encode(tables, stream_symbols=0, **kw)[0]         # one stock stream
-        fixed = coder.rans_encode(tables, stream_symbols=4096, **kw)[0]
+        fixed = coder.rans_encode(tables, stream_symbols=4096, lanes=1, **kw)[0]
         est = len(raw)                                        # what the likelihood sum predicts
-        auto = coder.rans_encode(tables, est_bytes=est, **kw)[0]
+        auto = coder.rans_encode(tables, est_bytes=est, lanes=1, **kw)[0]
         S = coder.stream_symbols_of(auto, L)
         n_streams = (L + S - 1) // S
         assert S == coder.auto_stream_symbols(L, est) and S % 256 == 0
@@ -485,3 +504,139 @@ def test_golden_reference_bitstreams(cuda_dev, golden_dir):
     assert torch.equal(q1.float().cpu(), torch.from_numpy(z["q1"]))
     y_hat = coder.decode_stage_b(q0, q1, means, prior)
     assert torch.equal(y_hat.cpu(), torch.from_numpy(z["y_hat"]))
+
+
+# ---------------------------------------------------------------------------
+# the lane-interleaved layouts ('DVC3', 'DVS3'): 32 stock rans64 coders per sub-stream
+# ---------------------------------------------------------------------------
+def _floor_heavy_latents(shape, seed, dev, floor_frac, exception_frac):
+    """Scales mostly at the 0.11 floor (marked table rows), symbols drawn from the model,
+    plus a few symbols a marked row does not expect."""
+    g = torch.Generator().manual_seed(seed)
+    scales = torch.exp(torch.empty(shape).uniform_(np.log(0.05), np.log(40), generator=g))
+    scales[torch.rand(shape, generator=g) < floor_frac] = 0.05
+    x = torch.round(torch.randn(shape, generator=g) * scales.clamp_min(0.11))
+    wrong = (torch.rand(shape, generator=g) < exception_frac) & (scales <= 0.11)
+    x[wrong] = torch.randint(-3, 4, shape, generator=g).float()[wrong]
+    return x.to(dev), scales.to(dev)
+
+
+@pytest.mark.parametrize("shape,S,floor,skip", [
+    ((1, 1, 1, 1), 1024, 0.0, True), ((2, 6, 10, 14), 256, 0.5, True),
+    ((2, 6, 10, 14), 100, 0.5, False), ((1, 3, 5, 7), 4096, 0.9, True),
+    ((1, 4, 33, 31), 1024, 0.97, True), ((2, 5, 41, 50), 3000, 0.97, True),
+    ((1, 32, 68, 120), 32768, 0.9, True), ((1, 32, 68, 120), 5000, 0.0, False)])
+def test_lane_interleaved_container_matches_oracle(cuda_dev, gc_pair, shape, S, floor, skip,
+                                                   monkeypatch):
+    """Byte for byte against the sequential CPU restatement of the layout
+    (oracle/c/rans_ref.c::dvcref_ilv_encode over the stock per-symbol arithmetic); the oracle
+    decodes the GPU's bytes, the GPU decodes its own, with the table look-up fused (scales)
+    and with explicit indexes."""
+    from deepvideocodec_b200 import coder
+    from oracle import rans
+    o, p = gc_pair
+    tables = p._tables()
+    cdf, size, off = _oracle_tables(o)
+    marks = rans.skip_rows_of(cdf, size, off)
+    assert torch.equal(tables.skip_rows().cpu(), torch.from_numpy(marks))
+    assert marks[0] == 1 and marks[-1] == 0 and 1 <= marks.sum() <= 4
+    x, scales = _floor_heavy_latents(shape, S + shape[1], cuda_dev, floor, 0.01)
+    L = shape[1] * shape[2] * shape[3]
+    flat = x.view(shape[0], -1)
+    for pos, val in ((0, 5.0), (31, -2.0), (32, 70000.0), (1023, -4000.0), (1024, 1.0), (L - 1, -1e6)):
+        if pos < L:
+            flat[0, pos] = val                                # escapes at group / chunk / stream edges
+    kw = dict(x=x, scales=scales, scale_table=p.scale_table, scale_bound=0.11)
+    got = coder.rans_encode(tables, stream_symbols=S, lanes=32, skip=skip, **kw)
+    S = -(-S // 1024) * 1024                                 # sub-streams are whole 1 024-position chunks
+    idx = o.build_indexes(scales.cpu()).numpy().reshape(shape[0], -1)
+    sym = x.int().cpu().numpy().reshape(shape[0], -1)
+    for n in range(shape[0]):
+        want = rans.encode_container(sym[n], idx[n], cdf, size, off, S, 32, marks if skip else None)
+        assert got[n] == want, (n, len(got[n]), len(want))
+        assert coder.container_of(got[n], L) == (S, 32, skip)
+        assert np.array_equal(
+            rans.decode_container(got[n], idx[n], cdf, size, off, marks if skip else None), sym[n])
+    out = coder.rans_decode(got, tables, shape, scales=scales, scale_table=p.scale_table,
+                            scale_bound=0.11, device=cuda_dev)
+    assert torch.equal(out, x)
+    syms = coder.rans_decode(got, tables, shape, indexes=torch.from_numpy(idx).to(cuda_dev).reshape(
+        shape), want_symbols=True)
+    assert torch.equal(syms, x.int())
+    # the inverse look-up that brackets the decoder's CDF search: its definition, and the same
+    # symbols without it (mode probe + 4-ary search)
+    lut = tables.cdf_lut().cpu().numpy()
+    for r in (0, 1, 17, 40, 63):
+        row = cdf[r, :size[r]]
+        want_lut = [int(np.searchsorted(row, 1024 * b, side="right")) - 1 for b in range(64)]
+        assert lut[r].tolist() == want_lut + [int(size[r]) - 2]
+    monkeypatch.setattr(coder.Tables, "cdf_lut", lambda self: None)
+    assert torch.equal(coder.rans_decode(got, tables, shape, scales=scales,
+                                         scale_table=p.scale_table, scale_bound=0.11,
+                                         device=cuda_dev), x)
+
+
+def test_lane_interleaved_entropy_bottleneck_and_errors(cuda_dev, gc_pair, eb_pair):
+    """Channel-indexed tables (EntropyBottleneck) with medians; malformed sub-streams are flagged
+    (a lane-interleaved sub-stream must end on the encoder's initial states)."""
+    from deepvideocodec_b200 import coder
+    from oracle import rans
+    eo, ep = eb_pair
+    z = (torch.randn(2, 64, 17, 30, generator=torch.Generator().manual_seed(15)) * 6).to(cuda_dev)
+    z[1, 3, 0, :2] += torch.tensor([900.0, -900.0], device=cuda_dev)
+    med = ep._get_medians().detach().reshape(1, -1, 1, 1)
+    s = coder.rans_encode(ep._tables(), x=z, means=med.expand_as(z), stream_symbols=8192, lanes=32)
+    cdf, size, off = _oracle_tables(eo)
+    marks = rans.skip_rows_of(cdf, size, off)
+    sym = torch.round(z - med).int().cpu().numpy().reshape(2, -1)
+    idx = np.repeat(np.arange(64, dtype=np.int32), 17 * 30)
+    for n in range(2):
+        assert s[n] == rans.encode_container(sym[n], idx, cdf, size, off, 8192, 32, marks)
+    back = coder.rans_decode(s, ep._tables(), z.shape, means=med, device=cuda_dev)
+    assert torch.equal(back, torch.round(z - med) + med)
+    # corrupt payload word / truncated container / wrong layout for the magic
+    w = bytearray(s[0])
+    w[-5] ^= 0x40
+    with pytest.raises(ValueError, match="malformed"):
+        coder.rans_decode([bytes(w), s[1]], ep._tables(), z.shape, means=med, device=cuda_dev)
+    with pytest.raises(ValueError, match="malformed"):
+        coder.rans_decode([s[0][:-8], s[1]], ep._tables(), z.shape, means=med, device=cuda_dev)
+    # the status word is per launch: the next call succeeds
+    assert torch.equal(coder.rans_decode(s, ep._tables(), z.shape, means=med, device=cuda_dev), back)
+    o, p = gc_pair
+    y, means, scales = _latents((1, 4, 6, 8), 7, cuda_dev)
+    with pytest.raises(Exception, match="lanes"):
+        coder.rans_encode(p._tables(), x=y, means=means, scales=scales, scale_table=p.scale_table,
+                          lanes=7)
+
+
+def test_lane_interleaved_payload_policy(cuda_dev, gc_pair):
+    """32 chains cost ~200 bytes: the sub-stream count follows the payload (1 % overhead
+    target), one sub-stream at the low end -- where implied zeros keep the chain short and cost
+    no more bytes than the stock stream codes them with."""
+    from deepvideocodec_b200 import coder
+    _, p = gc_pair
+    tables = p._tables()
+    g = torch.Generator().manual_seed(78)
+    shape = (1, 48, 68, 120)
+    L = shape[1] * shape[2] * shape[3]
+    for lo, hi, label in ((0.05, 0.11, "floor"), (0.16, 0.2, "low"), (4.0, 32.0, "high")):
+        scales = (torch.empty(shape).uniform_(lo, hi, generator=g)).to(cuda_dev)
+        x = torch.round(torch.randn(shape, generator=g).to(cuda_dev) * scales.clamp_min(0.11))
+        kw = dict(x=x, scales=scales, scale_table=p.scale_table, scale_bound=0.11)
+        raw = coder.rans_encode(tables, stream_symbols=0, **kw)[0]
+        est = len(raw)
+        auto = coder.rans_encode(tables, est_bytes=est, **kw)[0]
+        S, lanes, skip = coder.container_of(auto, L)
+        assert (lanes, skip) == (32, True) and S == coder.auto_stream_symbols(L, est, 32)
+        assert S % 1024 == 0
+        n_streams = (L + S - 1) // S
+        overhead = len(auto) - len(raw)
+        assert overhead <= 0.0125 * len(raw) + 280, (label, overhead, len(raw))
+        if label != "high":
+            assert n_streams == 1
+        else:
+            assert n_streams >= 8
+        out = coder.rans_decode([auto], tables, shape, scales=scales, scale_table=p.scale_table,
+                                scale_bound=0.11, device=cuda_dev)
+        assert torch.equal(out, x)

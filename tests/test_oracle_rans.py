@@ -278,3 +278,40 @@ def test_product_coder_refuses_cpu_tensors():
     fresh = dvc.GaussianConditional(None)
     with pytest.raises(ValueError, match="update"):
         fresh.compress(y, torch.zeros(1, 2, 4, 4, dtype=torch.int32))
+
+
+def test_lane_interleaved_restatement_round_trip_and_known_answer():
+    """The repository's own lane-interleaved sub-stream (oracle/c/rans_ref.c::dvcref_ilv_*):
+    round trips, and a hand-computed stream for a single symbol: mask word, 32 one-word states,
+    lane 0 = the stock state after one Rans64EncPut, the other lanes untouched at 2^31."""
+    rng = np.random.default_rng(11)
+    rows = [rans.pmf_to_quantized_cdf(np.array(p, dtype=np.float32)) for p in (
+        [3e-5, 1 - 7e-5, 3e-5, 1e-5], [0.1, 0.2, 0.39, 0.2, 0.1, 0.01], [1 / 41] * 41)]
+    cdf = np.zeros((3, max(len(r) for r in rows)), np.int32)
+    for i, r in enumerate(rows):
+        cdf[i, :len(r)] = r
+    sizes = np.array([len(r) for r in rows], np.int32)
+    offs = np.array([-1, -2, -20], np.int32)
+    marks = rans.skip_rows_of(cdf, sizes, offs)
+    assert marks.tolist() == [1, 0, 0]
+    for L in (1, 32, 33, 1023, 1024, 1025, 3000):
+        for p_floor in (0.0, 0.6, 0.98):
+            idx = np.where(rng.random(L) < p_floor, 0, rng.integers(1, 3, L)).astype(np.int32)
+            sym = np.where(idx == 0, (rng.random(L) < 0.01) * rng.integers(-3, 4, L),
+                           rng.integers(-30, 31, L)).astype(np.int32)
+            sym[rng.random(L) < 0.01] = 123456               # bypass-coded
+            for sk in (None, marks):
+                b = rans.ilv_encode(sym, idx, cdf, sizes, offs, sk)
+                assert np.array_equal(rans.ilv_decode(b, idx, cdf, sizes, offs, sk), sym)
+                c = rans.encode_container(sym, idx, cdf, sizes, offs, 700, 32, sk)
+                assert np.array_equal(rans.decode_container(c, idx, cdf, sizes, offs, sk), sym)
+    # known answer: symbol value 1 of row 1 (table position 3): start = cdf[1][3], freq = next - start
+    start, freq = int(cdf[1, 3]), int(cdf[1, 4] - cdf[1, 3])
+    x = ((1 << 31) // freq << 16) + (1 << 31) % freq + start
+    assert (1 << 32) <= x < (1 << 63)                        # p = 0.2: the state needs its high word
+    want = np.array([1, x & 0xFFFFFFFF, x >> 32] + [1 << 31] * 31, dtype=np.uint32).tobytes()
+    assert rans.ilv_encode(np.array([1]), np.array([1]), cdf, sizes, offs) == want
+    # a truncated stream is rejected by the restatement's end-state check
+    b = rans.ilv_encode(np.arange(-20, 20), np.full(40, 2), cdf, sizes, offs)
+    with pytest.raises(RuntimeError):
+        rans.ilv_decode(b[:-4], np.full(40, 2), cdf, sizes, offs)

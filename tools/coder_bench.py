@@ -6,7 +6,7 @@ For each sub-stream length S: CUDA-event time of the encode launches (kernel
 only, streams stay on the device), of the decode launches, the coded size and
 its container overhead; next to it the plain-C oracle coder (one host thread,
 the arithmetic CompressAI runs on the CPU; its Python list marshalling is NOT
-included, so this flatters the CPU side) on the same symbols.  Two regimes:
+included, so this flatters the CPU side) on the same symbols.  Three regimes ("matched" = the sparse scales with symbols drawn from the model itself):
 "synthetic" (SURVEY.md 8d latents, sigma in [0.05, 32]: ~3 bits/symbol) and
 "sparse" (97 % of the scales at the 0.11 floor and a spatial prior that predicts
 y: what a trained codec at low rate produces), because the overhead of sub-streams only shows
@@ -89,10 +89,19 @@ def main():
     inp = synthetic_pframe_inputs(1088, 1920, dev, seed=7)
     out = {"gpu": torch.cuda.get_device_name(0), "regimes": {}}
     with torch.no_grad():
-        for regime in ("synthetic", "sparse"):
-            jobs, pairs = planes_of(inp, gc, regime == "sparse")
+        for regime in ("synthetic", "sparse", "matched"):
+            jobs, pairs = planes_of(inp, gc, regime != "synthetic")
+            if regime == "matched":
+                # symbols drawn from the model the coder uses for them (what a trained codec
+                # produces): q = round(N(0, max(scale, 0.11))) on the sparse regime's scale planes
+                g = torch.Generator(device=dev).manual_seed(5)
+                for q, sc in pairs:
+                    q.copy_(torch.round(torch.randn(q.shape, device=dev, generator=g) *
+                                        sc.clamp_min(0.11)))
+                jobs = [(f"{lab}.y{k}", pairs[m][0][k:k + 1], pairs[m][1][k:k + 1])
+                        for m, lab in enumerate(("motion", "frame")) for k in (0, 1)]
             zs = [inp["motion.z"], inp["frame.z"]]
-            if regime == "sparse":
+            if regime != "synthetic":
                 zs = [z * 0.1 for z in zs]
             n_sym = sum(q.numel() for _, q, _ in jobs) + sum(z.numel() for z in zs)
             res = {"symbols_per_frame": n_sym, "sweep": []}
@@ -115,19 +124,34 @@ def main():
             res["cpu_c_oracle"] = {"encode_ms": 1e3 * t_enc, "decode_ms": 1e3 * t_dec,
                                    "bytes": sum(len(s) for s in stock), "threads": 1}
             res["bits_per_symbol"] = 8 * sum(len(s) for s in stock) / n_sym
-            for S in (256, 1024, 4096, 16384, 65536, "auto"):
-                def enc(S=S):
+            # per-tensor payload estimates (what the likelihood kernel's sum ln p gives the
+            # product for free): here the stock stream sizes of the same symbols, per pass
+            est_pairs = [(len(stock[0]) + len(stock[1])) / 2.0, (len(stock[2]) + len(stock[3])) / 2.0]
+            rows = [dict(label=f"dvc1_S{S}", S=S, lanes=1, skip=False, est=False)
+                    for S in (256, 1024, 4096, 16384)]
+            rows += [dict(label="dvc1_payload", S=None, lanes=1, skip=False, est=True)]
+            rows += [dict(label=f"dvc3_S{S}", S=S, lanes=32, skip=False, est=False)
+                     for S in (8192, 32768, 131072)]
+            rows += [dict(label=f"dvs3_S{S}", S=S, lanes=32, skip=True, est=False)
+                     for S in (8192, 32768, 131072)]
+            rows += [dict(label="dvc3_payload", S=None, lanes=32, skip=False, est=True),
+                     dict(label="dvs3_payload (product default)", S=None, lanes=32, skip=True, est=True)]
+            for row in rows:
+                def enc(row=row):
                     # both checkerboard passes of a model = one launch (as the product does);
-                    # "auto" = the product's defaults: per-tensor sub-stream length
-                    # (coder.auto_stream_symbols) and the z coder on the side stream
-                    auto = S == "auto"
+                    # S = None: the product's policy (coder.auto_stream_symbols, payload-driven
+                    # for the y tensors) and the z coder on the side stream
+                    auto = row["S"] is None
                     ps = [coder.rans_encode_async(eb._tables(), x=z, means=med.expand_as(z),
-                                                  stream_symbols=None if auto else S, overlap=auto)
+                                                  stream_symbols=row["S"], overlap=auto,
+                                                  lanes=row["lanes"], skip=row["skip"])
                           for z in zs]
                     ps = [coder.rans_encode_async(gc._tables(), x=q, scales=s,
                                                   scale_table=gc.scale_table,
-                                                  stream_symbols=None if auto else S)
-                          for q, s in pairs] + ps
+                                                  stream_symbols=row["S"], lanes=row["lanes"],
+                                                  skip=row["skip"],
+                                                  est_bytes=est_pairs[k] if row["est"] else None)
+                          for k, (q, s) in enumerate(pairs)] + ps
                     for p in ps:
                         if p.done is not None:
                             torch.cuda.current_stream().wait_event(p.done)
@@ -139,21 +163,39 @@ def main():
                 nbytes = sum(len(b) for s in strings for b in s)
                 strings = [[strings[0][0]], [strings[0][1]], [strings[1][0]], [strings[1][1]],
                            strings[2], strings[3]]
-                # decode: time the launches only (streams pre-staged on the device is not
-                # offered by the Python face, so this includes the small H2D of the strings)
+                # decode: the six launches one after the other, as a decoder has to run them
+                # (streams pre-staged on the device is not offered by the Python face, so this
+                # includes the small H2D of the strings)
                 def dec():
+                    outs, sts = [], []
                     for (name, q, s), st in zip(jobs, strings[:4]):
-                        coder.rans_decode(st, gc._tables(), q.shape, scales=s,
-                                          scale_table=gc.scale_table, want_symbols=True)
+                        outs.append(coder.rans_decode(st, gc._tables(), q.shape, scales=s,
+                                                      scale_table=gc.scale_table, want_symbols=True,
+                                                      statuses=sts))
                     for z, st in zip(zs, strings[4:]):
-                        coder.rans_decode(st, eb._tables(), z.shape, means=med)
+                        outs.append(coder.rans_decode(st, eb._tables(), z.shape, means=med,
+                                                      statuses=sts))
+                    coder.check_decode_status(sts)       # one host read, as the context models do
+                    return outs
+                outs = dec()
+                ok = all(torch.equal(o, q.int()) for o, (_, q, _) in zip(outs[:4], jobs)) and \
+                    all(torch.equal(o, torch.round(z - med) + med) for o, z in zip(outs[4:], zs))
                 t_d = ev_time(dec, iters=10)
                 res["sweep"].append({
-                    "S": S, "encode_launch_ms": t_e, "encode_with_d2h_ms": 1e3 * t_e2e,
+                    "layout": row["label"],
+                    "stream_symbols_y": [coder.stream_symbols_of(st[0], q.numel())
+                                         for (_, q, _), st in zip(jobs, strings[:4])],
+                    "round_trip_exact": bool(ok),
+                    "encode_launch_ms": t_e, "encode_with_d2h_ms": 1e3 * t_e2e,
                     "decode_with_h2d_ms": t_d, "bytes": nbytes,
                     "overhead_vs_stock_pct": 100.0 * (nbytes - res["cpu_c_oracle"]["bytes"]) /
                     res["cpu_c_oracle"]["bytes"],
-                    "Msym_per_s_encode": n_sym / t_e / 1e3})
+                    "Msym_per_s_encode": n_sym / t_e / 1e3, "Msym_per_s_decode": n_sym / t_d / 1e3})
+                r = res["sweep"][-1]
+                print(f"  {regime:10s} {r['layout']:32s} S={r['stream_symbols_y'][0]:<7d} "
+                      f"enc {r['encode_launch_ms']:7.3f} ms  dec {r['decode_with_h2d_ms']:7.3f} ms  "
+                      f"{r['bytes']:8d} B ({r['overhead_vs_stock_pct']:+.2f} %)  ok={ok}",
+                      file=sys.stderr)
             out["regimes"][regime] = res
     print(json.dumps(out, indent=1))
 
