@@ -133,11 +133,11 @@ _SIGNATURES = {
     "dvc_rans_encode": (
         c_int, [c_void_p] * 6 + [c_int64, c_float] + [c_void_p] * 3 + [c_int64] * 2 +
         [c_void_p, c_int64, c_void_p, c_void_p, c_void_p] + [c_int64] * 4 + [_P4] * 3 +
-        [c_int64, c_int, c_void_p, c_void_p]),
+        [c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "dvc_rans_decode": (
         c_int, [c_void_p, c_int64, c_void_p] + [c_void_p] * 3 + [c_int64, c_float] +
         [c_void_p] * 3 + [c_int64] * 2 + [c_void_p] * 4 + [c_int64] * 4 + [_P4] * 3 +
-        [c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+        [c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dvc_dual_prior_decode_stage_a": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [_P4] * 3 + [c_void_p]),
     "dvc_dual_prior_decode_stage_b": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [_P4] * 3 + [c_void_p]),
 }

@@ -47,6 +47,8 @@ STREAM_OVERHEAD_BYTES = 12             # per sub-stream: 4 B length word + 8 B r
 LANES_OVERHEAD_BYTES = 200             # lanes = 32: length + mask words + 32 states of 1-2 words
 LANES_STREAM_SYMBOLS = 65536           # lanes = 32, payload unknown: 2 048 rounds per sub-stream
 LANES_CHUNK = 1024                     # positions per chunk of the lane-interleaved kernels
+SKIP_FLAG_BUDGET = 0.005               # adaptive implied zeros: set flags may cost this share of the payload
+SKIP_FLAG_BITS = 12.0                  #   at ~12 bits each
 OVERHEAD_TARGET = float(os.environ.get("DVC_RANS_OVERHEAD", "0.01"))
 
 
@@ -151,32 +153,91 @@ class Tables:
             pass
         return marks
 
-    def cdf_lut(self):
-        """int16 ``[n_cdf, 65]`` on the device (read as uint16 by the kernel), or
-        ``None`` for tables the kernel does not stage (more than 256 rows, rows
-        longer than 32 767): ``lut[r, b] = max j with cdf[r, j] <= 1024 b`` for
-        ``b < 64``, ``lut[r, 64] = cdf_length[r] - 2``.  It brackets the decoder's
-        CDF search (``dvc_rans_decode(cdf_lut)``) and never changes a result.
-        Cached on the CDF buffer like ``skip_rows``."""
+    def cdf_pack(self):
+        """``(blob, entries)``: the tables re-packed for the decoder's shared memory
+        (``dvc_rans_decode(cdf_pack)``, layout in include/dvc_b200.h) -- a look-up
+        from the 16-bit ``cum`` to the range of table positions it can fall in
+        (``_lut_ranges``), the row offsets, and the rows back to back as uint16
+        ``(value - 1) mod 2^16`` with 4 pad entries each -- or ``(None, 0)`` for tables the kernel does not stage
+        (more than 256 rows, more than 124 KB).  Never changes a result.  Cached on
+        the CDF buffer."""
         key = (self.cdf._version, self.size.data_ptr(), self.size._version)
-        hit = getattr(self.cdf, "_dvc_cdf_lut", None)
+        hit = getattr(self.cdf, "_dvc_cdf_pack", None)
         if hit is not None and hit[0] == key:
             return hit[1]
         n, width = self.cdf.shape
-        lut = None
-        if n <= 256 and width <= 32767:
-            cols = torch.arange(width, device=self.cdf.device)
-            rows = torch.where(cols[None, :] < self.size[:, None].long(), self.cdf,
-                               torch.full_like(self.cdf, 1 << 17))          # sorted rows
-            thr = (torch.arange(64, device=self.cdf.device, dtype=torch.int32) * 1024)
-            idx = torch.searchsorted(rows, thr.expand(n, 64).contiguous(), right=True) - 1
-            lut = torch.cat((idx.to(torch.int32), (self.size - 2)[:, None]), 1)
-            lut = lut.clamp_(min=0).to(torch.int16).contiguous()
+        out = (None, 0)
+        sizes = self.size.long()
+        total = int(sizes.sum().item()) + PACK_PAD * n
+        start_off = n * LUT_KEYS * 4
+        tbl_off = start_off + 4 * n
+        nbytes = (tbl_off + 2 * total + 15) // 16 * 16
+        if n <= 256 and nbytes <= PACK_MAX_BYTES and int(sizes.min().item()) >= 2 and width < 65536:
+            dev = self.cdf.device
+            cols = torch.arange(width, device=dev)
+            inside = cols[None, :] < sizes[:, None]
+            rows = torch.where(inside, self.cdf, torch.full_like(self.cdf, 1 << 17))   # sorted rows
+            cmin, cmax = (torch.from_numpy(v).to(dev).expand(n, LUT_KEYS).contiguous()
+                          for v in _lut_ranges())
+            lo = (torch.searchsorted(rows, cmin, right=True) - 1).clamp_(min=0)
+            hi = torch.minimum(torch.searchsorted(rows, cmax, right=True), sizes[:, None] - 1)
+            lut = (lo | (hi << 16)).to(torch.int32)
+            starts = torch.cumsum(sizes + PACK_PAD, 0) - (sizes + PACK_PAD)
+            blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            blob[:start_off] = lut.contiguous().view(torch.uint8).reshape(-1)
+            blob[start_off:tbl_off] = starts.to(torch.int32).contiguous().view(torch.uint8).reshape(-1)
+            # (value - 1) mod 2^16, PACK_PAD entries 0xffff after every row
+            padded = torch.cat((rows, torch.full((n, PACK_PAD), 1 << 17, dtype=rows.dtype, device=dev)), 1)
+            keep = torch.arange(width + PACK_PAD, device=dev)[None, :] < (sizes + PACK_PAD)[:, None]
+            vals = torch.where(padded > 65536, torch.full_like(padded, 65536), padded)
+            flat = ((vals[keep] - 1) & 0xFFFF).to(torch.int32)
+            flat = torch.where(flat > 32767, flat - 65536, flat).to(torch.int16)
+            blob[tbl_off:tbl_off + 2 * total] = flat.contiguous().view(torch.uint8).reshape(-1)
+            out = (blob, total)
         try:
-            self.cdf._dvc_cdf_lut = (key, lut)
+            self.cdf._dvc_cdf_pack = (key, out)
         except AttributeError:
             pass
-        return lut
+        return out
+
+
+LUT_KEYS = 152                  # keys of the decoder's look-up (csrc/dvc_coder.cu::lut_key)
+PACK_PAD = 4                    # entries 0xffff after every packed row
+PACK_MAX_BYTES = 124 * 1024
+
+
+def lut_key(cum):
+    """Key of a 16-bit ``cum`` in the decoder's look-up: ``cum >> 10`` in the central part;
+    less than 2048 counts from either end, 16 exact keys then 4 per octave of the distance."""
+    up = cum >> 15
+    d = 65535 - cum if up else cum
+    if d >= 2048:
+        return cum >> 10
+    t = d
+    if d >= 16:
+        e = d.bit_length() - 1
+        t = 16 + ((e - 4) << 2) + ((d >> (e - 2)) & 3)
+    return 64 + t + 44 * up
+
+
+def _lut_ranges():
+    """``(cmin, cmax)`` int32 ``[LUT_KEYS]``: the ``cum`` values of every key (unused keys
+    cover everything)."""
+    cmin = np.zeros(LUT_KEYS, dtype=np.int32)
+    cmax = np.full(LUT_KEYS, 65535, dtype=np.int32)
+    for k in range(2, 62):
+        cmin[k], cmax[k] = 1024 * k, 1024 * k + 1023
+    for up in (0, 1):
+        for t in range(44):
+            if t < 16:
+                dmin = dmax = t
+            else:
+                e, m = 4 + (t - 16) // 4, (t - 16) % 4
+                dmin = (1 << e) + m * (1 << (e - 2))
+                dmax = dmin + (1 << (e - 2)) - 1
+            k = 64 + t + 44 * up
+            cmin[k], cmax[k] = (65535 - dmax, 65535 - dmin) if up else (dmin, dmax)
+    return cmin, cmax
 
 
 def pmf_to_quantized_cdf(pmf, precision=16):
@@ -287,10 +348,13 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
 
     ``lanes`` (default ``DVC_RANS_LANES`` = 32): 32 = every sub-stream is coded by
     32 lane-interleaved rans64 coders (``DVC3``), 1 = one stock stream per
-    sub-stream (``DVC1``).  ``skip`` (default ``DVC_RANS_SKIP`` = on; lanes = 32
-    only): symbols of (almost) deterministic table rows are coded as one flag per
-    group of 32 (``DVS3``), which shortens the serial chain by up to 32x on them --
-    most of a low-rate P-frame.  Both are ignored for a raw stock stream
+    sub-stream (``DVC1``).  ``skip`` (lanes = 32 only): symbols of (almost)
+    deterministic table rows are coded as one flag per group of 32 (``DVS3``),
+    which shortens the serial chain by up to 32x on them -- most of a low-rate
+    P-frame.  ``True`` forces it, ``False`` turns it off, the default (``None``,
+    with ``DVC_RANS_SKIP`` on) lets the encoder decide on the device: it counts
+    the flags that would be set and falls back to ``DVC3`` when they would cost
+    more than 0.5 % of the payload.  Both are ignored for a raw stock stream
     (``stream_symbols == 0``); all layouts are lossless.
 
     ``overlap=True`` runs the encoder on a per-device side stream (ordered after
@@ -324,8 +388,19 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
         lanes = 1                                   # raw stock stream
     if lanes == 32:                                 # sub-streams are whole chunks of 1 024 positions
         stream_symbols = -(-int(stream_symbols) // LANES_CHUNK) * LANES_CHUNK
+    # skip: True = always use the marks, None (default) = let the encoder count the groups a
+    # flag would be set in and use the marks only when those flags stay within SKIP_FLAG_BUDGET
+    # of the estimated payload (data the tables do not describe would otherwise grow), False = off
+    adaptive = skip is None
     skip = (DEFAULT_SKIP if skip is None else bool(skip)) and lanes == 32
     marks = tables.skip_rows() if skip else None
+    max_flagged = -1
+    if skip and adaptive:
+        if est_bytes is not None:
+            max_flagged = int(SKIP_FLAG_BUDGET * 8.0 * float(est_bytes) * n / SKIP_FLAG_BITS)
+        else:
+            max_flagged = n * L // 8192
+        max_flagged = max(max_flagged, n * L // 65536)      # a handful is never worth a fallback
     if marks is not None:
         keep = keep + [marks]
     lib = nat.lib()
@@ -349,7 +424,8 @@ def rans_encode_async(tables, x=None, means=None, symbols=None, indexes=None, sc
             tables.cdf.data_ptr(), tables.size.data_ptr(), tables.offset.data_ptr(),
             tables.cdf.size(0), tables.cdf.size(1), out.data_ptr(), cap, out_bytes.data_ptr(),
             scratch.data_ptr(), status.data_ptr(), n, c, h, w, nat.opt_st4(x),
-            nat.opt_st4(means), sst, int(stream_symbols), lanes, nat.ptr(marks), stream)
+            nat.opt_st4(means), sst, int(stream_symbols), lanes, nat.ptr(marks),
+            int(max_flagged), stream)
         if overlap:
             done = torch.cuda.Event()
             done.record(side)
@@ -455,7 +531,7 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
         raise ValueError("bit streams of one batch were written with different layouts")
     S, lanes, skip = S.pop()
     marks = tables.skip_rows() if skip else None
-    lut = tables.cdf_lut() if lanes == 32 else None
+    pack, pack_entries = tables.cdf_pack() if lanes == 32 else (None, 0)
     for s in strings:
         if len(s) < 8 or len(s) % 4:
             raise ValueError("truncated bit stream")
@@ -487,8 +563,8 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
             tables.cdf.size(0), tables.cdf.size(1), nat.ptr(means), nat.ptr(out_f),
             nat.ptr(out_s), status.data_ptr(), n, c, h, w, sst, nat.opt_st4(means),
             nat.opt_st4(out_f), int(S), -1 if cb is None else int(cb[0]),
-            0 if cb is None else int(cb[1]), lanes, nat.ptr(marks), nat.ptr(lut),
-            nat.ptr(scratch), nat.stream_of(buf))
+            0 if cb is None else int(cb[1]), lanes, nat.ptr(marks), nat.ptr(pack),
+            int(pack_entries), nat.ptr(scratch), nat.stream_of(buf))
     nat.check(rc, "dvc_rans_decode")
     if statuses is not None:
         statuses.append(status)

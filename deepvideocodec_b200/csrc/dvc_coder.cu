@@ -298,6 +298,10 @@ struct PackP {
   long long L, S;
   int n_streams, cap, header;  // header = 1: container, 0: raw stock stream
   uint32_t magic;
+  // adaptive implied zeros: magic_alt is written instead when *flagged > flagged_max
+  uint32_t magic_alt;
+  const unsigned* flagged;
+  long long flagged_max;
 };
 
 __global__ void __launch_bounds__(128) rans_pack_kernel(const PackP p) {
@@ -329,7 +333,8 @@ __global__ void __launch_bounds__(128) rans_pack_kernel(const PackP p) {
   const uint32_t mine = cnt[j];
   if (p.header) {
     if (j == 0 && threadIdx.x < 4) {
-      const uint32_t hdr[4] = {p.magic, (uint32_t)p.L, (uint32_t)p.S, (uint32_t)p.n_streams};
+      const uint32_t magic = (p.flagged && (long long)*p.flagged > p.flagged_max) ? p.magic_alt : p.magic;
+      const uint32_t hdr[4] = {magic, (uint32_t)p.L, (uint32_t)p.S, (uint32_t)p.n_streams};
       dst[threadIdx.x] = hdr[threadIdx.x];
     }
     if (threadIdx.x == 0) dst[4 + j] = mine;
@@ -355,7 +360,8 @@ struct DecP {
   Source src;                 // indexes / scales / means (symbols, x unused)
   Tables tb;
   const uint8_t* skip;        // [opt] lane-interleaved layout ('DVS3'): byte per table row
-  const uint16_t* lut;        // [opt] lane-interleaved layout: inverse look-up [n_cdf][65]
+  const uint16_t* pack;       // [opt] lane-interleaved layout: packed look-up + CDF rows
+  int pack_entries;
   const IlvDecChunk* ilv_dec; // lane-interleaved layout: pass-1 items of every chunk (prepare kernel)
   const uint16_t* ilv_ci;     //   table row of every position
   int32_t* ilv_sym;           //   decoded symbols [N][L]
@@ -565,10 +571,45 @@ constexpr uint32_t kMagic3S = 0x33535644u;   // "DVS3": + implied-zero groups
 constexpr int kIlvChunk = 1024;              // positions per chunk (32 groups x 32 lanes)
 constexpr int kIlvItems = kIlvChunk + 32;    // + one flag per group
 constexpr int kRowCache = 256;               // table rows whose size/offset/mark live in shared memory
-constexpr int kLutBuckets = 64;              // inverse-CDF look-up: 64 buckets of 1024 counts per row
-constexpr int kLutStride = kLutBuckets + 1;
+// Inverse-CDF look-up of the decoder: `cum` (16 bits) -> a key -> the first and one past the
+// last table position a symbol with such a `cum` can have.  Keys 2..61: cum >> 10 (1024 counts
+// each) for the central part; both ends (less than 2048 counts from 0 / from 65535) are split
+// logarithmically -- 16 exact keys, then 4 per octave -- because that is where a row has many
+// symbols per count: 44 keys per end.
+constexpr int kLutEnd = 44;
+constexpr int kLutStride = 64 + 2 * kLutEnd;  // u32 (lo | hi << 16) per key; keys 0, 1, 62, 63 unused
+__host__ __device__ inline int lut_key(uint32_t cum) {
+  const uint32_t up = cum >> 15;                         // 1: upper half
+  const uint32_t d = up ? 65535u - cum : cum;            // distance from the nearer end
+#ifdef __CUDA_ARCH__
+  const int e = 31 - __clz((int)(d | 16u));              // >= 4
+#else
+  int e = 4;
+  while (((d | 16u) >> (e + 1)) != 0u) ++e;
+#endif
+  const uint32_t t_log = 16u + ((uint32_t)(e - 4) << 2) + ((d >> (e - 2)) & 3u);
+  const uint32_t t = d < 16u ? d : t_log;
+  return (int)(d >= 2048u ? cum >> 10 : 64u + t + up * (uint32_t)kLutEnd);
+}
+constexpr int kPackPad = 4;                  // entries after every packed row, so that four probes never leave it
+constexpr int kPackMaxBytes = 124 * 1024;    // largest packed table the decoder stages in shared memory
 constexpr int kIlvRing = 5;                  // chunks in flight between the copy engine and the chain
 constexpr unsigned kFull = 0xffffffffu;
+
+// The decoder's packed tables (`cdf_pack`, built by the caller from the CDF tables, see
+// include/dvc_b200.h): u32 lut[n][152], u32 row_start[n], u16 cdf[total] holding (value - 1) mod
+// 2^16 -- "cum >= value" is "cum > stored", 65536 fits, and value = (stored + 1) [mod 2^16 for the
+// row's leading 0] -- each row followed by kPackPad entries 0xffff.
+struct PackLayout {
+  int start_off, tbl_off, bytes;   // byte offsets of row_start / cdf, total size (multiple of 16)
+};
+__host__ __device__ inline PackLayout pack_layout(int n_cdf, int total) {
+  PackLayout q;
+  q.start_off = n_cdf * kLutStride * 4;
+  q.tbl_off = q.start_off + 4 * n_cdf;
+  q.bytes = ((q.tbl_off + 2 * total + 15) / 16) * 16;
+  return q;
+}
 
 // ---- PTX wrappers: mbarrier + 1-D bulk copy (the copy engine fills the chain's stages) -------
 __device__ __forceinline__ uint32_t ilv_smem_u32(const void* p) {
@@ -664,9 +705,40 @@ struct IlvPrepP {
   IlvEncChunk* enc;                // encoder: [N * chunks_per_sample]
   IlvDecChunk* dec;                // decoder
   uint16_t* pos_ci;                // decoder: table row of every position [N][chunks_per_sample * 1024]
+  int32_t* sym_out;                // decoder: [N][L]; implied zeros are written here
+  const uint32_t* row_start;       // decoder [opt]: row offsets of the packed table
+  // encoder, adaptive implied zeros: groups that would be flagged (counted by ilv_count_kernel);
+  // above flagged_max the marks are ignored and the container is a plain 'DVC3'
+  unsigned* flagged;
+  long long flagged_max;
   int chunks_per_sample;
   int* status;
 };
+
+// ---- adaptive implied zeros: how many groups would carry a set flag ------------------------------
+// A set flag costs ~8-13 bits on top of coding the group's symbols; on data the tables describe
+// that is a fraction of a per cent of a per cent, on data they do not (marked rows full of
+// non-zero symbols) it would inflate the stream, so the encoder counts first and only uses the
+// marks when the flags stay within the caller's budget.
+__global__ void __launch_bounds__(kIlvChunk) ilv_count_kernel(const IlvPrepP p) {
+  __shared__ IlvRows R;
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x / p.chunks_per_sample;
+  const int c = blockIdx.x - n * p.chunks_per_sample;
+  ilv_load_rows(R, p.src, p.tb, p.skip);
+  __syncthreads();
+  const long long e = (long long)c * kIlvChunk + threadIdx.x;
+  bool nz = false;
+  if (e < p.src.L) {
+    int ch, h, w;
+    split_chw(p.src, e, ch, h, w);
+    const int ci = fetch_index(p.src, n, e, ch, h, w, R.tab);
+    if (ci >= 0 && ci < p.tb.n_cdf && ilv_marked(R, p.skip, ci))
+      nz = fetch_symbol(p.src, n, e, ch, h, w) != 0;
+  }
+  const int any = __syncthreads_count(__any_sync(kFull, nz) && lane == 0);   // flagged groups of the chunk
+  if (threadIdx.x == 0 && any) atomicAdd(p.flagged, (unsigned)any);
+}
 
 // ---- prepare: one chunk per CTA, warp g = group g, lane = position in the group ---------------
 template <bool kEncoder>
@@ -678,7 +750,8 @@ __global__ void __launch_bounds__(kIlvChunk) ilv_prepare_kernel(const IlvPrepP p
   const int n = blockIdx.x / p.chunks_per_sample;
   const int c = blockIdx.x - n * p.chunks_per_sample;
   if (threadIdx.x == 0) { any_esc = 0; any_mark = 0; }
-  ilv_load_rows(R, p.src, p.tb, p.skip);
+  const bool use_marks = !kEncoder || !p.flagged || (long long)*p.flagged <= p.flagged_max;
+  ilv_load_rows(R, p.src, p.tb, use_marks ? p.skip : nullptr);
   __syncthreads();
   const long long e = (long long)c * kIlvChunk + threadIdx.x;
   const bool valid = e < p.src.L;
@@ -689,7 +762,7 @@ __global__ void __launch_bounds__(kIlvChunk) ilv_prepare_kernel(const IlvPrepP p
     if (kEncoder) sym = fetch_symbol(p.src, n, e, ch, h, w);
     ci = fetch_index(p.src, n, e, ch, h, w, R.tab);
     if (ci < 0 || ci >= p.tb.n_cdf) { bad = true; ci = 0; }
-    sk = ilv_marked(R, p.skip, ci);
+    sk = ilv_marked(R, use_marks ? p.skip : nullptr, ci);
   }
   const uint32_t m_sk = __ballot_sync(kFull, sk);
   const uint32_t m_rg = __ballot_sync(kFull, valid && !sk);
@@ -767,9 +840,12 @@ __global__ void __launch_bounds__(kIlvChunk) ilv_prepare_kernel(const IlvPrepP p
   } else {
     IlvDecChunk& O = p.dec[blockIdx.x];
     if (valid) p.pos_ci[(long long)blockIdx.x * kIlvChunk + threadIdx.x] = (uint16_t)ci;
+    if (valid && sk) p.sym_out[(long long)n * p.src.L + e] = 0;   // unless its group turns out flagged
     if (slot >= 0)
-      O.item[slot] = make_uint4((uint32_t)((long long)ci * p.tb.cdf_stride), (uint32_t)max(so.x, 2),
-                                (uint32_t)so.y, (uint32_t)threadIdx.x | ((uint32_t)ci << 16));
+      O.item[slot] = make_uint4(p.row_start ? __ldg(p.row_start + ci)
+                                            : (uint32_t)((long long)ci * p.tb.cdf_stride),
+                                (uint32_t)max(so.x, 2), (uint32_t)so.y,
+                                (uint32_t)threadIdx.x | ((uint32_t)ci << 16));
     if (lane == 0) {
       O.skm[g] = m_sk;
       if (m_sk)
@@ -936,19 +1012,22 @@ __global__ void __launch_bounds__(32) rans_ilv_encode_kernel(const EncP p) {
 // ---- decoder chain ------------------------------------------------------------
 struct IlvDecShared {
   IlvDecChunk stage[kIlvRing];
-  unsigned long long bar[kIlvRing];
+  unsigned long long bar[kIlvRing + 1];   // + the packed tables
   IlvRows rows;                    // pass 2 only
-  int val[kIlvChunk];              // values of a chunk that has marked positions
   uint4 item2[kIlvChunk];          // pass 2, built from the decoded flags
   uint32_t flag[32];
-  uint16_t lut[8];                 // [min(n_cdf, kRowCache)][kLutStride] when a LUT is given
+  alignas(16) uint16_t pack[8];    // the packed tables (kPack)
 };
+static_assert(offsetof(IlvDecShared, pack) % 16 == 0, "bulk-copy destination");
 
 struct IlvDecState {
   unsigned long long x;
   const uint32_t* wp;   // words of this sub-stream
   int wn, base;         // their number; next unread word
   bool malformed;
+#ifdef DVC_ILV_PROF
+  long long prof[3];
+#endif
   __device__ __forceinline__ uint32_t word(int i) const {
     return (i < wn) ? __ldg(wp + i) : 0u;   // a corrupt stream reads zeros, never out of bounds
   }
@@ -956,22 +1035,33 @@ struct IlvDecState {
 
 constexpr uint32_t kIdleItem = 0xffffu;   // position field of an idle lane
 
-// One pass.  `direct`: the chunk has no marked position -- item k is position k and its value
-// goes straight to global memory (coalesced); otherwise values are collected in shared memory.
-template <bool kLut>
-__device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, const uint4* items,
-                                                int n_items, int32_t* direct, IlvDecState& D,
+// One pass of a chunk.  Decoded values go straight to global memory (`out` = the chunk's slice
+// of the symbol tensor; in a chunk without marked positions item k is position k: coalesced).
+// kPack: look-up and CDF rows come from the packed tables in shared memory.
+template <bool kPack, bool kFlags>
+__device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, const uint32_t* lut,
+                                                const uint16_t* tbl, const uint4* items,
+                                                int n_items, int32_t* out, IlvDecState& D,
                                                 int lane) {
   if (n_items <= 0) return;
   const unsigned lt = (1u << lane) - 1u;
   const uint4 idle = make_uint4(0u, 2u, 0u, kIdleItem);
   uint4 cur = lane < n_items ? items[lane] : idle;
   uint32_t window = D.word(D.base + lane);   // the next 32 words, one per lane
+#ifdef DVC_ILV_PROF
+  long long q0, q1;
+#define QF(k) q1 = clock64(); D.prof[k] += q1 - q0; q0 = q1;
+#else
+#define QF(k)
+#endif
   for (int r0 = 0; r0 < n_items; r0 += 32) {
+#ifdef DVC_ILV_PROF
+    q0 = clock64();
+#endif
     const uint4 nxt = r0 + 32 + lane < n_items ? items[r0 + 32 + lane] : idle;
     const uint32_t it = cur.w & 0xffffu;
     const bool act = it != kIdleItem;
-    const bool isflag = act && it >= (uint32_t)kIlvChunk;
+    const bool isflag = kFlags && act && it >= (uint32_t)kIlvChunk;
     const int size = (int)cur.y;
     const uint32_t cum = (uint32_t)(D.x & 0xffffu);  // Rans64DecGet
     // s = max j in [0, size-1) with row[j] <= cum  (row[0] = 0, row[size-1] = 2^16).
@@ -982,27 +1072,45 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
       if (cum >= cur.x) { lo = 1; start = cur.x; }
       else next = cur.x;
     } else if (act) {
-      const int32_t* __restrict__ row = p.tb.cdf + cur.x;
       int hi = size - 1;
       next = 0u;
-      if (kLut) {
-        // the look-up brackets the symbol: s(cum) in [lut[b], lut[b + 1]] for b = cum >> 10
-        const uint16_t* lut = S.lut + (cur.w >> 16) * kLutStride + (cum >> 10);
-        lo = lut[0];
-        hi = lut[1] + 1;
-        const uint32_t a0 = (uint32_t)__ldg(row + lo), a1 = (uint32_t)__ldg(row + lo + 1);
-        start = a0;
-        if (cum >= a1) { lo += 1; start = a1; }
-        else { hi = lo + 1; next = a1; }
+      if (kPack) {
+        // the look-up brackets the symbol: row[lo] <= cum < row[hi]; the next four positions
+        // are probed at once, which settles nearly every symbol without a loop
+        const uint32_t br = lut[(cur.w >> 16) * kLutStride + lut_key(cum)];
+        lo = (int)(br & 0xffffu);
+        hi = (int)(br >> 16);
+        const uint16_t* r = tbl + cur.x + lo;
+        const uint32_t b0 = r[0], b1 = r[1], b2 = r[2], b3 = r[3], b4 = r[4];
+        const int k = (cum > b1 ? 1 : 0) + (cum > b2 ? 1 : 0) + (cum > b3 ? 1 : 0);
+        uint32_t sm1 = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
+        uint32_t nm1 = k == 0 ? b1 : (k == 1 ? b2 : (k == 2 ? b3 : b4));
+        lo += k;
+        if (cum > b4) {        // beyond the probes (rare): bisect (lo + 1, hi), lo + 1 = 4th probe
+          lo += 1; sm1 = b4; nm1 = 0u;
+          bool have_next = false;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            const uint32_t v = tbl[cur.x + mid];
+            if (cum > v) { lo = mid; sm1 = v; }
+            else { hi = mid; nm1 = v; have_next = true; }
+          }
+          if (!have_next) nm1 = tbl[cur.x + hi];
+        }
+        start = (sm1 + 1u) & 0xffffu;
+        next = nm1 + 1u;
+      } else {
+        const int32_t* __restrict__ row = p.tb.cdf + cur.x;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          const uint32_t v = (uint32_t)__ldg(row + mid);
+          if (cum >= v) { lo = mid; start = v; }
+          else { hi = mid; next = v; }
+        }
+        if (next == 0u) next = (uint32_t)__ldg(row + hi);
       }
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        const uint32_t v = (uint32_t)__ldg(row + mid);
-        if (cum >= v) { lo = mid; start = v; }
-        else { hi = mid; next = v; }
-      }
-      if (next == 0u) next = (uint32_t)__ldg(row + hi);
     }
+    QF(0)
     // Rans64DecAdvance
     if (act) D.x = (unsigned long long)(next - start) * (D.x >> 16) + cum - start;
     {
@@ -1012,6 +1120,7 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
       if (need) D.x = (D.x << 32) | wv;
       D.base += __popc(m);
     }
+    QF(1)
     // bypass (Rans64DecGetBits(4) chain): one operation per lane and step, lanes in order
     const bool esc = act && !isflag && lo == size - 2;
     uint32_t raw = 0;
@@ -1049,16 +1158,15 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
           if (raw & 1u) value = -value - 1;
           else value += size - 2;
         }
-        value += (int)cur.z;
-        if (direct) direct[it] = value;
-        else S.val[it] = value;
+        out[it] = value + (int)cur.z;
       }
     }
     cur = nxt;
+    QF(2)
   }
 }
 
-template <bool kLut>
+template <bool kPack>
 __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
   extern __shared__ __align__(128) unsigned char ilv_smem[];
   IlvDecShared& S = *reinterpret_cast<IlvDecShared*>(ilv_smem);
@@ -1069,9 +1177,14 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
   const int n_chunks = (int)((s_end - s_begin + kIlvChunk - 1) / kIlvChunk);
   const long long first_chunk = (long long)n * p.chunks_per_sample + s_begin / kIlvChunk;
   const IlvDecChunk* first = p.ilv_dec + first_chunk;
+  const PackLayout pl = pack_layout(p.tb.n_cdf, p.pack_entries);
   if (lane == 0) {
-    for (int s = 0; s < kIlvRing; ++s) ilv_mbar_init(ilv_smem_u32(&S.bar[s]), 1);
+    for (int s = 0; s <= kIlvRing; ++s) ilv_mbar_init(ilv_smem_u32(&S.bar[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (kPack) {
+      ilv_mbar_expect_tx(ilv_smem_u32(&S.bar[kIlvRing]), (uint32_t)pl.bytes);
+      ilv_bulk_g2s(ilv_smem_u32(S.pack), p.pack, (uint32_t)pl.bytes, ilv_smem_u32(&S.bar[kIlvRing]));
+    }
     for (int i = 0; i < min(kIlvRing - 1, n_chunks); ++i) {
       ilv_mbar_expect_tx(ilv_smem_u32(&S.bar[i]), (uint32_t)sizeof(IlvDecChunk));
       ilv_bulk_g2s(ilv_smem_u32(&S.stage[i]), first + i, (uint32_t)sizeof(IlvDecChunk),
@@ -1079,13 +1192,16 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     }
   }
   ilv_load_rows(S.rows, p.src, p.tb, p.skip);
-  if (kLut)
-    for (int i = lane; i < p.tb.n_cdf * kLutStride; i += 32) S.lut[i] = __ldg(p.lut + i);
   __syncwarp();
+  const uint32_t* const lut = reinterpret_cast<const uint32_t*>(S.pack);
+  const uint16_t* const tbl = S.pack + pl.tbl_off / 2;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(p.in + n * p.in_stride);
   const long long total_words = __ldg(p.in_bytes + n) >> 2;
   IlvDecState D;
   D.malformed = false;
+#ifdef DVC_ILV_PROF
+  D.prof[0] = D.prof[1] = D.prof[2] = 0;
+#endif
   {
     bool ok = total_words >= 4 + p.n_streams && __ldg(words) == (p.skip ? kMagic3S : kMagic3) &&
               __ldg(words + 1) == (uint32_t)p.src.L && __ldg(words + 2) == (uint32_t)p.S &&
@@ -1113,6 +1229,7 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     D.base = 33 + __popc(mask);
   }
   int32_t* const sym_out = p.ilv_sym + (long long)n * p.src.L;
+  if (kPack) ilv_mbar_wait(ilv_smem_u32(&S.bar[kIlvRing]), 0u);
 #ifdef DVC_ILV_PROF
   long long pf_wait = 0, pf_pass = 0, pf_t0 = clock64(), pf_a, pf_b;
 #endif
@@ -1131,47 +1248,44 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     ilv_mbar_wait(ilv_smem_u32(&S.bar[s]), (uint32_t)((i / kIlvRing) & 1));
     const IlvDecChunk& T = S.stage[s];
     const long long cb = s_begin + (long long)i * kIlvChunk;
-    const int n_valid = (int)min((long long)kIlvChunk, s_end - cb);
-    const int n1 = T.meta.n1;
-    const bool marks = (T.meta.flags & 2) != 0;
     PF(pf_wait)
-    if (!marks) {
-      // every position is a pass-1 item in position order
-      ilv_decode_pass<kLut>(p, S, T.item, n1, sym_out + cb, D, lane);
+    // pass 1: regular symbols and group flags
+    if (!(T.meta.flags & 2)) {
+      ilv_decode_pass<kPack, false>(p, S, lut, tbl, T.item, T.meta.n1, sym_out + cb, D, lane);
     } else {
-      for (int k = lane; k < kIlvChunk; k += 32) S.val[k] = 0;   // implied zeros
+      ilv_decode_pass<kPack, true>(p, S, lut, tbl, T.item, T.meta.n1, sym_out + cb, D, lane);
       __syncwarp();
-      ilv_decode_pass<kLut>(p, S, T.item, n1, nullptr, D, lane);
-      __syncwarp();
-      // pass 2: the marked symbols of the groups whose flag came out set (lane g <-> group g)
+      // pass 2: the marked symbols of the groups whose flag came out set (lane g <-> group g);
+      // the others keep the zeros the prepare kernel wrote
       const uint32_t skm = T.skm[lane];
       unsigned fm = __ballot_sync(kFull, skm != 0u && S.flag[lane] != 0u);
-      int n2 = 0;
-      while (fm) {
-        const int g = __ffs((int)fm) - 1;
-        fm &= fm - 1u;
-        const uint32_t sm = __shfl_sync(kFull, skm, g);
-        if ((sm >> lane) & 1u) {
-          const int pos = 32 * g + lane;
-          const int ci = __ldg(p.ilv_ci + (first_chunk + i) * kIlvChunk + pos);
-          const int2 so = ilv_size_off(S.rows, p.tb, ci);
-          S.item2[n2 + __popc(sm & ((1u << lane) - 1u))] =
-              make_uint4((uint32_t)((long long)ci * p.tb.cdf_stride), (uint32_t)max(so.x, 2),
-                         (uint32_t)so.y, (uint32_t)pos | ((uint32_t)ci << 16));
+      if (fm) {
+        int n2 = 0;
+        while (fm) {
+          const int g = __ffs((int)fm) - 1;
+          fm &= fm - 1u;
+          const uint32_t sm = __shfl_sync(kFull, skm, g);
+          if ((sm >> lane) & 1u) {
+            const int pos = 32 * g + lane;
+            const int ci = __ldg(p.ilv_ci + (first_chunk + i) * kIlvChunk + pos);
+            const int2 so = ilv_size_off(S.rows, p.tb, ci);
+            const uint32_t at = kPack ? reinterpret_cast<const uint32_t*>(S.pack + pl.start_off / 2)[ci]
+                                      : (uint32_t)((long long)ci * p.tb.cdf_stride);
+            S.item2[n2 + __popc(sm & ((1u << lane) - 1u))] =
+                make_uint4(at, (uint32_t)max(so.x, 2), (uint32_t)so.y, (uint32_t)pos | ((uint32_t)ci << 16));
+          }
+          n2 += __popc(sm);
         }
-        n2 += __popc(sm);
+        __syncwarp();
+        ilv_decode_pass<kPack, false>(p, S, lut, tbl, S.item2, n2, sym_out + cb, D, lane);
       }
-      __syncwarp();
-      ilv_decode_pass<kLut>(p, S, S.item2, n2, nullptr, D, lane);
-      __syncwarp();
-      for (int k = lane; k < n_valid; k += 32) sym_out[cb + k] = S.val[k];
     }
     PF(pf_pass)
   }
 #ifdef DVC_ILV_PROF
   if (lane == 0 && j == 0 && n == 0)
-    printf("dec chain: chunks %d total %lld wait %lld pass %lld\n", n_chunks, clock64() - pf_t0,
-           pf_wait, pf_pass);
+    printf("dec chain: chunks %d total %lld wait %lld pass %lld | search %lld advance %lld tail %lld\n",
+           n_chunks, clock64() - pf_t0, pf_wait, pf_pass, D.prof[0], D.prof[1], D.prof[2]);
 #endif
   // a well-formed sub-stream ends with every lane back at the encoder's initial state and
   // every word consumed
@@ -1412,7 +1526,7 @@ int64_t dvc_rans_scratch_bytes(int64_t N, int64_t L, int64_t stream_symbols, int
     return -1;
   int64_t bytes = N * (int64_t)q.n_streams * (int64_t)(q.cap + 1) * 4;
   if (lanes == 32)   // + the coder records of every chunk (prepare kernel -> chain kernel)
-    bytes = ((bytes + 15) / 16) * 16 + N * ((L + kIlvChunk - 1) / kIlvChunk) * (int64_t)sizeof(IlvEncChunk);
+    bytes = ((bytes + 15) / 16) * 16 + N * ((L + kIlvChunk - 1) / kIlvChunk) * (int64_t)sizeof(IlvEncChunk) + 16;
   return bytes;
 }
 
@@ -1440,7 +1554,7 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
                     int64_t N, int64_t C, int64_t H, int64_t W, const int64_t x_st[4],
                     const int64_t means_st[4], const int64_t scales_st[4],
                     int64_t stream_symbols, int lanes, const uint8_t* skip_rows,
-                    dvc_stream_t stream) {
+                    int64_t skip_max_flagged, dvc_stream_t stream) {
   DVC_REQUIRE((x != nullptr) != (symbols != nullptr),
               "rans_encode: give exactly one of x / symbols");
   DVC_REQUIRE(!skip_rows || lanes == 32, "rans_encode: skip_rows needs the lane-interleaved layout");
@@ -1463,6 +1577,8 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
   p.stream_data = p.stream_words + N * (int64_t)q.n_streams;
   p.status = status;
   p.skip = skip_rows;
+  const unsigned* flagged = nullptr;
+  long long flagged_max = 0;
   if (lanes == 32) {
     DVC_REQUIRE(n_cdf * cdf_stride < 2147483647LL, "rans_encode: CDF table too large");
     const int64_t cps = (p.src.L + kIlvChunk - 1) / kIlvChunk;
@@ -1471,7 +1587,21 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
     DVC_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15u) == 0, "rans_encode: scratch must be 16-byte aligned");
     IlvPrepP k;
     k.src = p.src; k.tb = p.tb; k.skip = skip_rows; k.enc = chunks; k.dec = nullptr; k.pos_ci = nullptr;
+    k.sym_out = nullptr; k.row_start = nullptr;
+    k.flagged = nullptr; k.flagged_max = 0;
     k.chunks_per_sample = (int)cps; k.status = status;
+    if (skip_rows && skip_max_flagged >= 0) {
+      // the counter lives behind the chunk records (dvc_rans_scratch_bytes reserves it)
+      k.flagged = reinterpret_cast<unsigned*>(chunks + N * cps);
+      k.flagged_max = skip_max_flagged;
+      cudaError_t e0 = cudaMemsetAsync(k.flagged, 0, sizeof(unsigned), (cudaStream_t)stream);
+      if (e0 != cudaSuccess)
+        return fail(DVC_ERR_CUDA, "rans_encode: cudaMemsetAsync: %s", cudaGetErrorString(e0));
+      ilv_count_kernel<<<(unsigned)(N * cps), kIlvChunk, 0, (cudaStream_t)stream>>>(k);
+      rc = check_launch("ilv_count_kernel");
+      if (rc) return rc;
+    }
+    flagged = k.flagged; flagged_max = k.flagged_max;
     ilv_prepare_kernel<true><<<(unsigned)(N * cps), kIlvChunk, 0, (cudaStream_t)stream>>>(k);
     rc = check_launch("ilv_prepare_kernel");
     if (rc) return rc;
@@ -1496,6 +1626,7 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
   k.out_bytes = reinterpret_cast<long long*>(out_bytes);
   k.L = p.src.L; k.S = q.S; k.n_streams = q.n_streams; k.cap = q.cap; k.header = q.header;
   k.magic = lanes == 32 ? (skip_rows ? kMagic3S : kMagic3) : kMagic;
+  k.magic_alt = kMagic3; k.flagged = flagged; k.flagged_max = flagged_max;
   rans_pack_kernel<<<dim3((unsigned)q.n_streams, (unsigned)N), 128, 0, (cudaStream_t)stream>>>(k);
   return check_launch("rans_pack_kernel");
 }
@@ -1508,7 +1639,8 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
                     int64_t H, int64_t W, const int64_t scales_st[4], const int64_t means_st[4],
                     const int64_t out_st[4], int64_t stream_symbols, int cb_parity,
                     int64_t cb_alt, int lanes, const uint8_t* skip_rows,
-                    const uint16_t* cdf_lut, void* scratch, dvc_stream_t stream) {
+                    const uint16_t* cdf_pack, int64_t cdf_pack_entries, void* scratch,
+                    dvc_stream_t stream) {
   DVC_REQUIRE(in && in_bytes, "rans_decode: null input");
   DVC_REQUIRE(!skip_rows || lanes == 32, "rans_decode: skip_rows needs the lane-interleaved layout");
   DVC_REQUIRE(cb_parity < 0 || (cb_parity <= 1 && scales),
@@ -1536,7 +1668,8 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
   p.S = q.S; p.n_streams = q.n_streams; p.header = q.header; p.N = (int)N;
   p.status = status;
   p.skip = skip_rows;
-  p.lut = nullptr;
+  p.pack = nullptr;
+  p.pack_entries = 0;
   if (lanes == 32) {
     DVC_REQUIRE(n_cdf * cdf_stride < 2147483647LL, "rans_decode: CDF table too large");
     DVC_REQUIRE(scratch && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0,
@@ -1549,18 +1682,28 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes, const int64_t* i
     uint16_t* pos_ci = reinterpret_cast<uint16_t*>(sp);
     sp += N * cps * kIlvChunk * 2;
     int32_t* syms = reinterpret_cast<int32_t*>(sp);
+    // the packed tables are staged in shared memory when they fit
+    if (cdf_pack && n_cdf <= kRowCache && cdf_pack_entries > 0 && cdf_pack_entries < (1 << 20) &&
+        pack_layout((int)n_cdf, (int)cdf_pack_entries).bytes <= kPackMaxBytes) {
+      DVC_REQUIRE((reinterpret_cast<uintptr_t>(cdf_pack) & 15u) == 0, "rans_decode: cdf_pack must be 16-byte aligned");
+      p.pack = cdf_pack;
+      p.pack_entries = (int)cdf_pack_entries;
+    }
+    const PackLayout pl = pack_layout((int)n_cdf, p.pack_entries);
+    p.ilv_sym = out_symbols ? out_symbols : syms;
     IlvPrepP k;
     k.src = p.src; k.tb = p.tb; k.skip = skip_rows; k.enc = nullptr; k.dec = chunks; k.pos_ci = pos_ci;
+    k.sym_out = p.ilv_sym;
+    k.flagged = nullptr; k.flagged_max = 0;
+    k.row_start = p.pack ? reinterpret_cast<const uint32_t*>(
+                               reinterpret_cast<const uint8_t*>(p.pack) + pl.start_off) : nullptr;
     k.chunks_per_sample = (int)cps; k.status = status;
     ilv_prepare_kernel<false><<<(unsigned)(N * cps), kIlvChunk, 0, (cudaStream_t)stream>>>(k);
     rc = check_launch("ilv_prepare_kernel");
     if (rc) return rc;
     p.ilv_dec = chunks; p.ilv_ci = pos_ci; p.chunks_per_sample = (int)cps;
-    p.ilv_sym = out_symbols ? out_symbols : syms;
-    // the look-up is staged in shared memory: only for tables of up to kRowCache rows
-    p.lut = (cdf_lut && n_cdf <= kRowCache) ? cdf_lut : nullptr;
-    const size_t smem = sizeof(IlvDecShared) + (p.lut ? (size_t)n_cdf * kLutStride * 2 : 0);
-    auto kern = p.lut ? rans_ilv_decode_kernel<true> : rans_ilv_decode_kernel<false>;
+    const size_t smem = sizeof(IlvDecShared) + (p.pack ? (size_t)pl.bytes : 0);
+    auto kern = p.pack ? rans_ilv_decode_kernel<true> : rans_ilv_decode_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess)

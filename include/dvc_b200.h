@@ -379,6 +379,10 @@ int dvc_symbols_indexes_fwd(const float* x, const float* means,
  * the group is not 0" with P(1) = 8k/65536; pass 2 codes the marked symbols of
  * the flagged groups with their own rows.  Unflagged marked symbols are 0 and
  * take no chain step.  Lossless; both layouts round-trip any int32 symbols.
+ * skip_max_flagged >= 0 makes the marks adaptive: the encoder first counts the
+ * groups whose flag would be set (each costs ~8-13 bits) and, above that
+ * number, ignores skip_rows and writes a plain 'DVC3' (all on the device; the
+ * decoder reads the magic).  -1: always use the marks.
  * lanes = 1: the 'DVC1' layout above.
  *
  * Symbols come from `symbols` (int32, contiguous [N][L]) or from `x` [N,C,H,W]
@@ -418,7 +422,8 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
                     void* scratch, int* status, int64_t N, int64_t C, int64_t H,
                     int64_t W, const int64_t x_st[4], const int64_t means_st[4],
                     const int64_t scales_st[4], int64_t stream_symbols,
-                    int lanes, const uint8_t* skip_rows, dvc_stream_t stream);
+                    int lanes, const uint8_t* skip_rows, int64_t skip_max_flagged,
+                    dvc_stream_t stream);
 /* Inverse.  in: device bytes (sample n at in + n*in_stride_bytes, in_bytes
  * device int64[N] = size of each container).  Writes out [opt] = float(symbol)
  * + means [opt] (EntropyModel.dequantize; strided [N,C,H,W]) and/or
@@ -427,10 +432,23 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
  * also: a sub-stream that does not end on the encoder's initial states with
  * every word consumed); a malformed container never reads out of bounds.
  * `lanes` / `skip_rows` must match the container's magic (the Python face
- * reads it).  cdf_lut [opt, lanes = 32, n_cdf <= 256]: device uint16
- * [n_cdf][65], an inverse look-up derived from the tables that brackets the
- * decoder's CDF search: cdf_lut[r][b] = max j with cdf[r][j] <= 1024 b for
- * b < 64, cdf_lut[r][64] = cdf_size[r] - 2.  Never changes the result. */
+ * reads it).  cdf_pack [opt, lanes = 32, n_cdf <= 256]: the tables re-packed
+ * for the decoder's shared memory, 16-byte aligned device memory, derived from
+ * the tables by the caller (cdf_pack_entries = number of u16 CDF entries):
+ *   u32 lut[n_cdf][152]  lo | hi << 16 per key of the 16-bit cum: the table
+ *                        positions [lo, hi) a symbol with such a cum can start at
+ *                        (cdf[r][lo] <= cum < cdf[r][hi]).  Keys 2..61 = cum >> 10;
+ *                        cums closer than 2048 to 0 (keys 64..107) or to 65535
+ *                        (108..151) by distance d: 16 exact keys, then 4 per
+ *                        octave of d (csrc/dvc_coder.cu::lut_key)
+ *   u32 row_start[n_cdf] offset of every row in the array below
+ *   u16 cdf[entries]     the rows back to back, (value - 1) mod 2^16 (so that
+ *                        "cum >= value" is "cum > stored" and 65536 fits), each
+ *                        row followed by 4 entries 0xffff; entries = sum of
+ *                        (cdf_size + 4)
+ * It never changes a result; without it (or when it exceeds 124 KB) the decoder
+ * searches the tables in global memory.  scratch: lanes = 32 only,
+ * dvc_rans_decode_scratch_bytes(N, L, S, lanes) bytes, 16-byte aligned. */
 int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes,
                     const int64_t* in_bytes, const int32_t* indexes,
                     const float* scales, const float* scale_table, int64_t T,
@@ -441,8 +459,8 @@ int dvc_rans_decode(const uint8_t* in, int64_t in_stride_bytes,
                     int64_t C, int64_t H, int64_t W, const int64_t scales_st[4],
                     const int64_t means_st[4], const int64_t out_st[4],
                     int64_t stream_symbols, int cb_parity, int64_t cb_alt,
-                    int lanes, const uint8_t* skip_rows, const uint16_t* cdf_lut,
-                    void* scratch, dvc_stream_t stream);
+                    int lanes, const uint8_t* skip_rows, const uint16_t* cdf_pack,
+                    int64_t cdf_pack_entries, void* scratch, dvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Decoder side of the checkerboard dual prior: the element-wise glue of

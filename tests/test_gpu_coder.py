@@ -190,7 +190,7 @@ def test_module_compress_decompress_match_oracle_modules(cuda_dev, gc_pair, eb_p
     # the default layout: 32 lane-interleaved coders per sub-stream, implied zeros on
     monkeypatch.setattr(coder, "DEFAULT_LANES", 32)
     s = p.compress(y, idx, means)
-    assert coder.container_of(s[0], 8 * 12 * 16) == (coder.LANES_STREAM_SYMBOLS, 32, True)
+    assert coder.container_of(s[0], 8 * 12 * 16)[:2] == (coder.LANES_STREAM_SYMBOLS, 32)
     assert torch.equal(p.decompress(s, idx, means=means), torch.round(y - means) + means)
 
     eo, ep = eb_pair
@@ -563,14 +563,28 @@ def test_lane_interleaved_container_matches_oracle(cuda_dev, gc_pair, shape, S, 
     syms = coder.rans_decode(got, tables, shape, indexes=torch.from_numpy(idx).to(cuda_dev).reshape(
         shape), want_symbols=True)
     assert torch.equal(syms, x.int())
-    # the inverse look-up that brackets the decoder's CDF search: its definition, and the same
-    # symbols without it (mode probe + 4-ary search)
-    lut = tables.cdf_lut().cpu().numpy()
+    # the packed tables the decoder stages in shared memory: their definition, and the same
+    # symbols without them (search in global memory)
+    blob, entries = tables.cdf_pack()
+    raw = blob.cpu().numpy().tobytes()
+    n_rows = cdf.shape[0]
+    assert entries == int(size.sum()) + 4 * n_rows
+    lut = np.frombuffer(raw, dtype=np.uint32, count=n_rows * coder.LUT_KEYS).reshape(n_rows, -1)
+    start_off = n_rows * coder.LUT_KEYS * 4
+    starts = np.frombuffer(raw, dtype=np.uint32, count=n_rows, offset=start_off)
+    packed = np.frombuffer(raw, dtype=np.uint16, count=entries, offset=start_off + 4 * n_rows)
+    assert np.array_equal(starts, np.cumsum(size + 4) - (size + 4))
+    rng = np.random.default_rng(S)
     for r in (0, 1, 17, 40, 63):
         row = cdf[r, :size[r]]
-        want_lut = [int(np.searchsorted(row, 1024 * b, side="right")) - 1 for b in range(64)]
-        assert lut[r].tolist() == want_lut + [int(size[r]) - 2]
-    monkeypatch.setattr(coder.Tables, "cdf_lut", lambda self: None)
+        assert np.array_equal(packed[starts[r]:starts[r] + size[r]], ((row - 1) & 0xFFFF).astype(np.uint16))
+        assert (packed[starts[r] + size[r]:starts[r] + size[r] + 4] == 0xFFFF).all()
+        # every cum falls inside the bracket of its key: row[lo] <= cum < row[hi]
+        for cum in list(range(0, 40)) + list(range(65496, 65536)) + rng.integers(0, 65536, 300).tolist():
+            br = int(lut[r, coder.lut_key(int(cum))])
+            lo, hi = br & 0xFFFF, br >> 16
+            assert row[lo] <= cum < row[hi] and hi <= size[r] - 1, (r, cum, lo, hi)
+    monkeypatch.setattr(coder.Tables, "cdf_pack", lambda self: (None, 0))
     assert torch.equal(coder.rans_decode(got, tables, shape, scales=scales,
                                          scale_table=p.scale_table, scale_bound=0.11,
                                          device=cuda_dev), x)
@@ -640,3 +654,33 @@ def test_lane_interleaved_payload_policy(cuda_dev, gc_pair):
         out = coder.rans_decode([auto], tables, shape, scales=scales, scale_table=p.scale_table,
                                 scale_bound=0.11, device=cuda_dev)
         assert torch.equal(out, x)
+
+
+def test_implied_zeros_are_adaptive(cuda_dev, gc_pair):
+    """Default (skip=None): the encoder counts, on the device, the groups whose flag would be
+    set and only uses the marks when those flags fit the budget -- data the tables describe
+    keeps 'DVS3', data they do not (marked rows full of non-zero symbols) falls back to a plain
+    'DVC3' that is no larger than coding without marks; forcing the marks there costs bytes."""
+    from deepvideocodec_b200 import coder
+    _, p = gc_pair
+    tables = p._tables()
+    shape = (1, 16, 68, 120)
+    L = shape[1] * shape[2] * shape[3]
+    for exc, want_skip in ((0.0, True), (0.05, False)):
+        x, scales = _floor_heavy_latents(shape, 91, cuda_dev, 0.9, exc)
+        kw = dict(x=x, scales=scales, scale_table=p.scale_table, scale_bound=0.11, stream_symbols=32768)
+        raw = coder.rans_encode(tables, **dict(kw, stream_symbols=0))[0]
+        auto = coder.rans_encode(tables, est_bytes=len(raw), **kw)[0]
+        plain = coder.rans_encode(tables, skip=False, **kw)[0]
+        forced = coder.rans_encode(tables, skip=True, **kw)[0]
+        assert coder.container_of(auto, L) == (32768, 32, want_skip)
+        assert coder.container_of(plain, L) == (32768, 32, False)
+        assert coder.container_of(forced, L) == (32768, 32, True)
+        if want_skip:
+            assert auto == forced and len(auto) <= len(plain) + 64
+        else:
+            assert auto == plain and len(forced) > len(plain) + 200
+        for s in (auto, plain, forced):
+            out = coder.rans_decode([s], tables, shape, scales=scales, scale_table=p.scale_table,
+                                    scale_bound=0.11, device=cuda_dev)
+            assert torch.equal(out, x)

@@ -135,7 +135,8 @@ def main():
             rows += [dict(label=f"dvs3_S{S}", S=S, lanes=32, skip=True, est=False)
                      for S in (8192, 32768, 131072)]
             rows += [dict(label="dvc3_payload", S=None, lanes=32, skip=False, est=True),
-                     dict(label="dvs3_payload (product default)", S=None, lanes=32, skip=True, est=True)]
+                     dict(label="dvs3_payload_forced", S=None, lanes=32, skip=True, est=True),
+                     dict(label="adaptive_payload (product default)", S=None, lanes=32, skip=None, est=True)]
             for row in rows:
                 def enc(row=row):
                     # both checkerboard passes of a model = one launch (as the product does);
@@ -183,6 +184,8 @@ def main():
                 t_d = ev_time(dec, iters=10)
                 res["sweep"].append({
                     "layout": row["label"],
+                    "container": [list(coder.container_of(st[0], q.numel())[1:])
+                                  for (_, q, _), st in zip(jobs, strings[:4])],
                     "stream_symbols_y": [coder.stream_symbols_of(st[0], q.numel())
                                          for (_, q, _), st in zip(jobs, strings[:4])],
                     "round_trip_exact": bool(ok),
@@ -193,7 +196,7 @@ def main():
                     "Msym_per_s_encode": n_sym / t_e / 1e3, "Msym_per_s_decode": n_sym / t_d / 1e3})
                 r = res["sweep"][-1]
                 print(f"  {regime:10s} {r['layout']:32s} S={r['stream_symbols_y'][0]:<7d} "
-                      f"enc {r['encode_launch_ms']:7.3f} ms  dec {r['decode_with_h2d_ms']:7.3f} ms  "
+                      f"{''.join('S' if c[1] else '-' for c in r['container'])} enc {r['encode_launch_ms']:7.3f} ms  dec {r['decode_with_h2d_ms']:7.3f} ms  "
                       f"{r['bytes']:8d} B ({r['overhead_vs_stock_pct']:+.2f} %)  ok={ok}",
                       file=sys.stderr)
             out["regimes"][regime] = res
