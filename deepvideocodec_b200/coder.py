@@ -9,11 +9,13 @@ real-bitstream path (``dmc/test.py:187-188`` -> ``DMC.encode_inter`` /
 construction behind ``DMC.update`` (``:669-677``).
 
 A bit stream returned here is a ``bytes`` object per batch sample, like
-CompressAI's.  With ``stream_symbols > 0`` it is the ``DVC1`` container (many
-stock rans64 sub-streams, one GPU warp each -- see ``include/dvc_b200.h``);
-with ``stream_symbols == 0`` it is one raw stock stream, byte-compatible with
-CompressAI's ``RansEncoder.encode_with_indexes``.  The decoder tells the two
-apart from the first word.
+CompressAI's.  With ``stream_symbols > 0`` it is one of this repository's
+containers around the stock rans64 arithmetic -- ``DVC3`` / ``DVS3`` (default:
+every sub-stream coded by the 32 lanes of one warp, optionally with implied zeros
+for near-deterministic table rows) or ``DVC1`` (one stock stream per sub-stream),
+see ``include/dvc_b200.h`` -- with ``stream_symbols == 0`` it is one raw stock
+stream, byte-compatible with CompressAI's ``RansEncoder.encode_with_indexes``.
+The decoder tells them apart from the first word.
 """
 import os
 import struct
@@ -55,21 +57,24 @@ OVERHEAD_TARGET = float(os.environ.get("DVC_RANS_OVERHEAD", "0.01"))
 def auto_stream_symbols(n_symbols, est_bytes=None, lanes=1):
     """Sub-stream length used when the caller does not choose one.
 
-    Range coding is serial inside a sub-stream, so a launch lasts
-    ``stream_symbols`` x the per-symbol chain latency no matter how few symbols
-    there are -- more sub-streams are faster -- but each sub-stream costs
-    ``STREAM_OVERHEAD_BYTES`` = 12 bytes.  A fixed length of 4 096 symbols is
-    +0.3 % bytes at 7 bits/symbol but +15 ... 80 % at the 0.03 - 0.15
-    bits/symbol of a low-rate P-frame, so the policy is driven by the
-    PAYLOAD: with an estimate of the coded size (the fused ``sum ln p`` of the
-    likelihood kernel, free in the fused context models) the number of
-    sub-streams is the largest that keeps the container overhead at
-    ``DVC_RANS_OVERHEAD`` (1 %) of the payload, but at least
-    ``DVC_RANS_MIN_STREAMS`` (8; 96 bytes) so that a near-empty tensor does not
-    decode as one serial chain.  Without an estimate the length is
-    ``DEFAULT_STREAM_SYMBOLS``; ``DVC_RANS_STREAM_SYMBOLS`` pins it (0 = one raw
-    stock stream, byte-compatible with CompressAI, for interop).  The length is
-    recorded in the container header, so decoders need no matching policy."""
+    Range coding is serial inside a chain, so more chains are faster, but every
+    chain costs its flush bytes.  The policy is driven by the PAYLOAD: with an
+    estimate of the coded size (the fused ``sum ln p`` of the likelihood kernel,
+    free in the fused context models) the number of sub-streams is the largest
+    that keeps the container overhead at ``DVC_RANS_OVERHEAD`` (1 %) of it.
+
+    ``lanes = 32`` (``DVC3`` / ``DVS3``, the default layout): a sub-stream is 32
+    chains for ~200 bytes and a whole number of 1024-position chunks; at least
+    one sub-stream (one warp: ``n_symbols / 32`` rounds, far fewer with implied
+    zeros); without an estimate ``LANES_STREAM_SYMBOLS``.
+    ``lanes = 1`` (``DVC1``): 12 bytes per chain; at least ``DVC_RANS_MIN_STREAMS``
+    (8; 96 bytes) so that a near-empty tensor does not decode as one serial chain;
+    without an estimate ``DEFAULT_STREAM_SYMBOLS``.  A fixed 4 096 symbols was
+    +0.3 % bytes at 7 bits/symbol but +15 ... 80 % at the 0.03 - 0.15 bits/symbol
+    of a low-rate P-frame.
+    ``DVC_RANS_STREAM_SYMBOLS`` pins a length (0 = one raw stock stream,
+    byte-compatible with CompressAI, for interop).  The length is recorded in the
+    container header, so decoders need no matching policy."""
     if PINNED_STREAM_SYMBOLS is not None:
         return PINNED_STREAM_SYMBOLS
     if lanes == 32 and DEFAULT_STREAM_SYMBOLS > 0:

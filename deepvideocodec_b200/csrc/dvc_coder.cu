@@ -1024,6 +1024,8 @@ struct IlvDecState {
   unsigned long long x;
   const uint32_t* wp;   // words of this sub-stream
   int wn, base;         // their number; next unread word
+  uint32_t window;      // words [base, base + 32), one per lane: a renormalising lane takes its
+                        // word with a shuffle instead of a dependent load
   bool malformed;
 #ifdef DVC_ILV_PROF
   long long prof[3];
@@ -1047,7 +1049,6 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
   const unsigned lt = (1u << lane) - 1u;
   const uint4 idle = make_uint4(0u, 2u, 0u, kIdleItem);
   uint4 cur = lane < n_items ? items[lane] : idle;
-  uint32_t window = D.word(D.base + lane);   // the next 32 words, one per lane
 #ifdef DVC_ILV_PROF
   long long q0, q1;
 #define QF(k) q1 = clock64(); D.prof[k] += q1 - q0; q0 = q1;
@@ -1116,7 +1117,7 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
     {
       const bool need = act && D.x < (1ull << 31);
       const unsigned m = __ballot_sync(kFull, need);
-      const uint32_t wv = __shfl_sync(kFull, window, __popc(m & lt));
+      const uint32_t wv = __shfl_sync(kFull, D.window, __popc(m & lt));
       if (need) D.x = (D.x << 32) | wv;
       D.base += __popc(m);
     }
@@ -1147,7 +1148,7 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
         }
       } while (__any_sync(kFull, ph != 0));
     }
-    window = D.word(D.base + lane);
+    D.window = D.word(D.base + lane);
     if (act) {
       if (isflag) {
         S.flag[it - kIlvChunk] = (uint32_t)lo;
@@ -1227,6 +1228,7 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     D.x = (unsigned long long)D.word(at);
     if ((mask >> lane) & 1u) D.x |= (unsigned long long)D.word(at + 1) << 32;
     D.base = 33 + __popc(mask);
+    D.window = D.word(D.base + lane);
   }
   int32_t* const sym_out = p.ilv_sym + (long long)n * p.src.L;
   if (kPack) ilv_mbar_wait(ilv_smem_u32(&S.bar[kIlvRing]), 0u);

@@ -4,7 +4,9 @@ ABI (``dvc_symbols_indexes_fwd``, ``dvc_rans_encode``, ``dvc_rans_decode``):
 * bit streams are compared BYTE FOR BYTE with the plain-C oracle
   (``oracle/c/rans_ref.c``): the raw mode (``stream_symbols = 0``) against one
   stock stream, the ``DVC1`` container sub-stream by sub-stream against stock
-  streams of the corresponding slices;
+  streams of the corresponding slices, the lane-interleaved ``DVC3`` / ``DVS3``
+  containers against the sequential restatement of their schedule
+  (``dvcref_ilv_encode``), which in turn decodes the GPU's bytes;
 * decode(encode(x)) == round(x - means) + means, also at BASELINE.json's full
   1080p latent sizes, where the coded size is additionally checked against the
   estimated rate of the likelihood kernels (a size-independent property);
