@@ -34,6 +34,13 @@
 // stream_symbols = 0 selects ONE raw stock stream without header, byte-
 // identical to CompressAI's RansEncoder.encode_with_indexes (interop mode,
 // serial: one warp per sample).
+//
+// That is the 'DVC1' layout (lanes = 1).  The default since round 2 is the
+// lane-interleaved layout further down ('DVC3' / 'DVS3', lanes = 32): 32 stock
+// rans64 coders per warp with a shared word stream, implied zeros for the
+// near-deterministic table rows, the data-parallel half in its own kernel.
+#include <stddef.h>
+
 #include "dvc_common.cuh"
 
 namespace dvc {
