@@ -334,11 +334,11 @@ __global__ void __launch_bounds__(128) rans_pack_kernel(const PackP p) {
   const long long head = p.header ? (4 + p.n_streams) : 0;
   const long long need = (head + (long long)total) * 4;
   const bool fits = need <= p.out_stride;
-  if (j == 0 && threadIdx.x == 0) p.out_bytes[n] = fits ? need : -need;
+  if (j == 0 && blockIdx.z == 0 && threadIdx.x == 0) p.out_bytes[n] = fits ? need : -need;
   if (!fits) return;
   uint32_t* dst = reinterpret_cast<uint32_t*>(p.out + n * p.out_stride);
   const uint32_t mine = cnt[j];
-  if (p.header) {
+  if (p.header && blockIdx.z == 0) {
     if (j == 0 && threadIdx.x < 4) {
       const uint32_t magic = (p.flagged && (long long)*p.flagged > p.flagged_max) ? p.magic_alt : p.magic;
       const uint32_t hdr[4] = {magic, (uint32_t)p.L, (uint32_t)p.S, (uint32_t)p.n_streams};
@@ -348,7 +348,9 @@ __global__ void __launch_bounds__(128) rans_pack_kernel(const PackP p) {
   }
   const uint32_t* src = p.stream_data + ((long long)n * p.n_streams + j + 1) * p.cap - mine;
   uint32_t* d = dst + head + before;
-  for (uint32_t i = threadIdx.x; i < mine; i += blockDim.x) d[i] = src[i];
+  // gridDim.z CTAs share the copy of a long sub-stream
+  for (uint32_t i = blockIdx.z * blockDim.x + threadIdx.x; i < mine; i += gridDim.z * blockDim.x)
+    d[i] = src[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -1636,7 +1638,10 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
   k.L = p.src.L; k.S = q.S; k.n_streams = q.n_streams; k.cap = q.cap; k.header = q.header;
   k.magic = lanes == 32 ? (skip_rows ? kMagic3S : kMagic3) : kMagic;
   k.magic_alt = kMagic3; k.flagged = flagged; k.flagged_max = flagged_max;
-  rans_pack_kernel<<<dim3((unsigned)q.n_streams, (unsigned)N), 128, 0, (cudaStream_t)stream>>>(k);
+  // long sub-streams (few of them) are copied by several CTAs each
+  const long long per_stream = (long long)q.S < 4096 ? 1 : ((long long)q.S + 4095) / 4096;
+  const unsigned slices = (unsigned)(per_stream > 32 ? 32 : per_stream);
+  rans_pack_kernel<<<dim3((unsigned)q.n_streams, (unsigned)N, slices), 128, 0, (cudaStream_t)stream>>>(k);
   return check_launch("rans_pack_kernel");
 }
 

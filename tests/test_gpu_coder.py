@@ -686,3 +686,34 @@ def test_implied_zeros_are_adaptive(cuda_dev, gc_pair):
             out = coder.rans_decode([s], tables, shape, scales=scales, scale_table=p.scale_table,
                                     scale_bound=0.11, device=cuda_dev)
             assert torch.equal(out, x)
+
+
+def test_lane_interleaved_decoder_survives_corrupt_streams(cuda_dev, gc_pair):
+    """Random byte flips anywhere in a valid 'DVS3' / 'DVC3' container: the decoder either
+    flags the stream (ValueError) or returns symbols -- it never faults, hangs or reads out of
+    bounds (every word read is bounds-checked, every loop is bounded by the table or by 64
+    bypass nibbles) -- and the next, clean, decode is unaffected."""
+    from deepvideocodec_b200 import coder
+    _, p = gc_pair
+    tables = p._tables()
+    shape = (1, 6, 40, 52)
+    rng = np.random.default_rng(5)
+    for skip, floor in ((True, 0.9), (False, 0.2)):
+        x, scales = _floor_heavy_latents(shape, 17, cuda_dev, floor, 0.002)
+        x.view(-1)[:4] = torch.tensor([900.0, -70000.0, 3.0, -5.0], device=cuda_dev)   # bypass-coded
+        kw = dict(scales=scales, scale_table=p.scale_table, scale_bound=0.11)
+        good = coder.rans_encode(tables, x=x, stream_symbols=4096, lanes=32, skip=skip, **kw)[0]
+        flagged = 0
+        for trial in range(48):
+            bad = bytearray(good)
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(16, len(bad)))           # keep the magic / L / S / n words
+                bad[pos] ^= int(rng.integers(1, 256))
+            try:
+                out = coder.rans_decode([bytes(bad)], tables, shape, device=cuda_dev, **kw)
+                assert out.shape == x.shape
+            except ValueError:
+                flagged += 1
+        torch.cuda.synchronize()
+        assert flagged >= 40                                    # the end-state check catches nearly all
+        assert torch.equal(coder.rans_decode([good], tables, shape, device=cuda_dev, **kw), x)
