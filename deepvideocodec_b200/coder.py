@@ -18,7 +18,9 @@ stream, byte-compatible with CompressAI's ``RansEncoder.encode_with_indexes``.
 The decoder tells them apart from the first word.
 """
 import os
+import functools
 import struct
+import threading
 
 import numpy as np
 import torch
@@ -103,6 +105,52 @@ def _side_stream(device):
         s = torch.cuda.Stream(device=device)
         _side_streams[device.index] = s
     return s
+
+
+class _PinnedRing:
+    """A few pinned host buffers per device and thread, reused round robin: slot k is handed
+    out again once the copy that last read it has completed (an event; normally long past).
+    torch's own pinned allocator is not used per call because a block freed while its copy is
+    still queued cannot be reused yet, and a fresh ``cudaHostAlloc`` costs more than the
+    decode it would feed."""
+
+    def __init__(self, slots=8):
+        self.bufs = [None] * slots
+        self.events = [None] * slots
+        self.k = 0
+
+    def take(self, nbytes):
+        k = self.k
+        self.k = (k + 1) % len(self.bufs)
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+            self.events[k] = None
+        b = self.bufs[k]
+        if b is None or b.numel() < nbytes:
+            size = 1 << max(16, int(nbytes - 1).bit_length())
+            b = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+            self.bufs[k] = b
+        return k, b
+
+    def release(self, k, stream):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self.events[k] = ev
+
+
+_staging_local = threading.local()
+
+
+def _staging(device):
+    rings = getattr(_staging_local, "rings", None)
+    if rings is None:
+        rings = _staging_local.rings = {}
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    r = rings.get(idx)
+    if r is None:
+        r = rings[idx] = _PinnedRing()
+    return r
 
 
 def _dev_i32(t, name):
@@ -213,35 +261,27 @@ PACK_MAX_BYTES = 124 * 1024
 
 def lut_key(cum):
     """Key of a 16-bit ``cum`` in the decoder's look-up: ``cum >> 10`` in the central part;
-    less than 2048 counts from either end, 16 exact keys then 4 per octave of the distance."""
+    less than 2048 counts from either end, four keys per octave of the distance ``d`` (the
+    exponent and the two leading mantissa bits of ``float(d | 1)``)."""
     up = cum >> 15
     d = 65535 - cum if up else cum
     if d >= 2048:
         return cum >> 10
-    t = d
-    if d >= 16:
-        e = d.bit_length() - 1
-        t = 16 + ((e - 4) << 2) + ((d >> (e - 2)) & 3)
-    return 64 + t + 44 * up
+    v = d | 1
+    e = v.bit_length() - 1
+    return 64 + 4 * e + (((v << 2) >> e) & 3) + 44 * up
 
 
+@functools.lru_cache(maxsize=1)
 def _lut_ranges():
-    """``(cmin, cmax)`` int32 ``[LUT_KEYS]``: the ``cum`` values of every key (unused keys
-    cover everything)."""
+    """``(cmin, cmax)`` int32 ``[LUT_KEYS]``: the ``cum`` values of every key (a contiguous
+    range each; unused keys cover everything)."""
     cmin = np.zeros(LUT_KEYS, dtype=np.int32)
     cmax = np.full(LUT_KEYS, 65535, dtype=np.int32)
-    for k in range(2, 62):
-        cmin[k], cmax[k] = 1024 * k, 1024 * k + 1023
-    for up in (0, 1):
-        for t in range(44):
-            if t < 16:
-                dmin = dmax = t
-            else:
-                e, m = 4 + (t - 16) // 4, (t - 16) % 4
-                dmin = (1 << e) + m * (1 << (e - 2))
-                dmax = dmin + (1 << (e - 2)) - 1
-            k = 64 + t + 44 * up
-            cmin[k], cmax[k] = (65535 - dmax, 65535 - dmin) if up else (dmin, dmax)
+    keys = np.fromiter((lut_key(c) for c in range(65536)), dtype=np.int64, count=65536)
+    edges = np.flatnonzero(np.diff(keys)) + 1
+    for a, b in zip(np.r_[0, edges], np.r_[edges, 65536]):
+        cmin[keys[a]], cmax[keys[a]] = a, b - 1
     return cmin, cmax
 
 
@@ -540,12 +580,25 @@ def rans_decode(strings, tables, shape, indexes=None, scales=None, scale_table=N
     for s in strings:
         if len(s) < 8 or len(s) % 4:
             raise ValueError("truncated bit stream")
-    stride = max(len(s) for s in strings)
-    host = np.zeros((n, stride), dtype=np.uint8)
+    # ONE pinned staging buffer per call -- the n sizes (int64), then the n streams at a common
+    # 16-byte-aligned stride -- and ONE asynchronous copy: no host synchronisation here, so
+    # the host side of the next launch (and whatever the caller queues) overlaps this one's
+    # serial chain.
+    stride = (max(len(s) for s in strings) + 15) // 16 * 16
+    head = (8 * n + 15) // 16 * 16
+    slot, stage = _staging(dev).take(head + n * stride)
+    host = stage.numpy()
+    host[:8 * n].view(np.int64)[:] = [len(s) for s in strings]
     for i, s in enumerate(strings):
-        host[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
-    buf = torch.from_numpy(host).to(dev, non_blocking=False)
-    in_bytes = torch.tensor([len(s) for s in strings], dtype=torch.int64, device=dev)
+        at = head + i * stride
+        host[at:at + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        host[at + len(s):at + stride] = 0
+    dbuf = torch.empty(head + n * stride, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        dbuf.copy_(stage[:head + n * stride], non_blocking=True)
+        _staging(dev).release(slot, torch.cuda.current_stream(dev))
+    in_bytes = dbuf[:8 * n].view(torch.int64)
+    buf = dbuf[head:].view(n, stride)
     ip, sp, tp, T, sst, keep = _index_args(indexes, scales, scale_table, (n, c, h, w), dev)
     if means is not None:
         means = means.to(device=dev, dtype=torch.float32).expand(n, c, h, w)

@@ -582,28 +582,29 @@ constexpr int kIlvItems = kIlvChunk + 32;    // + one flag per group
 constexpr int kRowCache = 256;               // table rows whose size/offset/mark live in shared memory
 // Inverse-CDF look-up of the decoder: `cum` (16 bits) -> a key -> the first and one past the
 // last table position a symbol with such a `cum` can have.  Keys 2..61: cum >> 10 (1024 counts
-// each) for the central part; both ends (less than 2048 counts from 0 / from 65535) are split
-// logarithmically -- 16 exact keys, then 4 per octave -- because that is where a row has many
-// symbols per count: 44 keys per end.
+// each) for the central part; both ends (d < 2048 counts from 0 / from 65535) are split
+// logarithmically, four keys per octave of d -- that is where a row has many symbols per
+// count: 44 keys per end.  The logarithmic key is the exponent and the two leading mantissa
+// bits of float(d | 1): one conversion and one shift.
 constexpr int kLutEnd = 44;
 constexpr int kLutStride = 64 + 2 * kLutEnd;  // u32 (lo | hi << 16) per key; keys 0, 1, 62, 63 unused
 __host__ __device__ inline int lut_key(uint32_t cum) {
   const uint32_t up = cum >> 15;                         // 1: upper half
   const uint32_t d = up ? 65535u - cum : cum;            // distance from the nearer end
 #ifdef __CUDA_ARCH__
-  const int e = 31 - __clz((int)(d | 16u));              // >= 4
+  const uint32_t t = (__float_as_uint(__uint2float_rn(d | 1u)) >> 21) - (127u << 2);
 #else
-  int e = 4;
-  while (((d | 16u) >> (e + 1)) != 0u) ++e;
+  uint32_t e = 0;
+  while (((d | 1u) >> (e + 1)) != 0u) ++e;
+  const uint32_t t = (e << 2) + ((((d | 1u) << 2) >> e) & 3u);
 #endif
-  const uint32_t t_log = 16u + ((uint32_t)(e - 4) << 2) + ((d >> (e - 2)) & 3u);
-  const uint32_t t = d < 16u ? d : t_log;
   return (int)(d >= 2048u ? cum >> 10 : 64u + t + up * (uint32_t)kLutEnd);
 }
 constexpr int kPackPad = 4;                  // entries after every packed row, so that four probes never leave it
 constexpr int kPackMaxBytes = 124 * 1024;    // largest packed table the decoder stages in shared memory
 constexpr int kIlvRing = 5;                  // chunks in flight between the copy engine and the chain
 constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kIdleItem = 0xffffu;       // position field of an idle item (decoder)
 
 // The decoder's packed tables (`cdf_pack`, built by the caller from the CDF tables, see
 // include/dvc_b200.h): u32 lut[n][152], u32 row_start[n], u16 cdf[total] holding (value - 1) mod
@@ -861,6 +862,9 @@ __global__ void __launch_bounds__(kIlvChunk) ilv_prepare_kernel(const IlvPrepP p
         O.item[flag_slot] = make_uint4((1u << 16) - 8u * (uint32_t)__popc(m_sk), 3u, 0u,
                                        (uint32_t)(kIlvChunk + g));
     }
+    // idle items up to a whole round of 32: the chain warp loads its items without a bound test
+    if (threadIdx.x < 32 && n1 + (int)threadIdx.x < ((n1 + 31) & ~31))
+      O.item[n1 + threadIdx.x] = make_uint4(0u, 2u, 0u, kIdleItem);
     if (threadIdx.x == 0) {
       IlvMeta m;
       m.n1 = n1; m.n2 = 0; m.flags = any_mark ? 2 : 0; m.pad = 0;
@@ -1035,6 +1039,8 @@ struct IlvDecState {
   int wn, base;         // their number; next unread word
   uint32_t window;      // words [base, base + 32), one per lane: a renormalising lane takes its
                         // word with a shuffle instead of a dependent load
+  int wbase;            // packed-table passes: `window` / `w1` hold words [wbase, wbase + 64),
+  uint32_t w1;          // 0 <= base - wbase < 32 between rounds
   bool malformed;
 #ifdef DVC_ILV_PROF
   long long prof[3];
@@ -1044,14 +1050,12 @@ struct IlvDecState {
   }
 };
 
-constexpr uint32_t kIdleItem = 0xffffu;   // position field of an idle lane
-
 // One pass of a chunk.  Decoded values go straight to global memory (`out` = the chunk's slice
 // of the symbol tensor; in a chunk without marked positions item k is position k: coalesced).
-// kPack: look-up and CDF rows come from the packed tables in shared memory.
-template <bool kPack, bool kFlags>
-__device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, const uint32_t* lut,
-                                                const uint16_t* tbl, const uint4* items,
+// This version bisects the CDF rows in global memory (tables too large to stage, or no
+// `cdf_pack` given); the packed-table version follows.
+template <bool kFlags>
+__device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, const uint4* items,
                                                 int n_items, int32_t* out, IlvDecState& D,
                                                 int lane) {
   if (n_items <= 0) return;
@@ -1084,41 +1088,14 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
     } else if (act) {
       int hi = size - 1;
       next = 0u;
-      if (kPack) {
-        // the look-up brackets the symbol: row[lo] <= cum < row[hi]; the next four positions
-        // are probed at once, which settles nearly every symbol without a loop
-        const uint32_t br = lut[(cur.w >> 16) * kLutStride + lut_key(cum)];
-        lo = (int)(br & 0xffffu);
-        hi = (int)(br >> 16);
-        const uint16_t* r = tbl + cur.x + lo;
-        const uint32_t b0 = r[0], b1 = r[1], b2 = r[2], b3 = r[3], b4 = r[4];
-        const int k = (cum > b1 ? 1 : 0) + (cum > b2 ? 1 : 0) + (cum > b3 ? 1 : 0);
-        uint32_t sm1 = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
-        uint32_t nm1 = k == 0 ? b1 : (k == 1 ? b2 : (k == 2 ? b3 : b4));
-        lo += k;
-        if (cum > b4) {        // beyond the probes (rare): bisect (lo + 1, hi), lo + 1 = 4th probe
-          lo += 1; sm1 = b4; nm1 = 0u;
-          bool have_next = false;
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            const uint32_t v = tbl[cur.x + mid];
-            if (cum > v) { lo = mid; sm1 = v; }
-            else { hi = mid; nm1 = v; have_next = true; }
-          }
-          if (!have_next) nm1 = tbl[cur.x + hi];
-        }
-        start = (sm1 + 1u) & 0xffffu;
-        next = nm1 + 1u;
-      } else {
-        const int32_t* __restrict__ row = p.tb.cdf + cur.x;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          const uint32_t v = (uint32_t)__ldg(row + mid);
-          if (cum >= v) { lo = mid; start = v; }
-          else { hi = mid; next = v; }
-        }
-        if (next == 0u) next = (uint32_t)__ldg(row + hi);
+      const int32_t* __restrict__ row = p.tb.cdf + cur.x;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t v = (uint32_t)__ldg(row + mid);
+        if (cum >= v) { lo = mid; start = v; }
+        else { hi = mid; next = v; }
       }
+      if (next == 0u) next = (uint32_t)__ldg(row + hi);
     }
     QF(0)
     // Rans64DecAdvance
@@ -1174,6 +1151,130 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
     cur = nxt;
     QF(2)
   }
+}
+
+// The same pass for the packed tables, written as ONE basic block per round.  The chain warp is
+// alone on its SM: nothing hides an instruction's latency except the independent instructions
+// the scheduler finds next to it, and every divergent branch of the version above (idle lanes,
+// the probe selection, the flag rows) both serialised its arms and stopped the compiler from
+// moving the round's off-chain work (next item, stores, word window) into the shadow of the
+// chain's loads and shuffles.  Here
+//   * an idle lane runs the chain arithmetic on the row {0, 2^16}: x' = 2^16 (x >> 16) + cum = x,
+//     so no predicate guards the search, the advance or the renormalisation;
+//   * the four probes are settled with a depth-2 tree of selects;
+//   * the two rare cases (symbol beyond the probes, bypass-coded value) sit behind warp-uniform
+//     votes;
+//   * the word window is 64 words deep (two registers per lane): the load that refills it is
+//     issued ~4 rounds before its first word is used instead of one round.
+// Same arithmetic, same word order: byte-for-byte the container of the encoder above.
+template <bool kFlags>
+__device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const uint32_t* lut,
+                                                       const uint16_t* tbl, const uint4* items,
+                                                       int n_items, int32_t* out, IlvDecState& D,
+                                                       int lane) {
+  if (n_items <= 0) return;
+  const unsigned lt = (1u << lane) - 1u;
+  // the item list is padded with idle items to a whole number of rounds (by whoever built it)
+  uint4 cur = items[lane];
+  int wbase = D.wbase;
+  uint32_t w0 = D.window, w1 = D.w1;
+  asm volatile("" : "+l"(out));   // keep the base in registers (otherwise re-derived every round)
+#pragma unroll 1
+  for (int r0 = 0; r0 < n_items; r0 += 32) {
+    uint4 nxt = cur;
+    if (r0 + 32 < n_items) nxt = items[r0 + 32 + lane];
+    const uint32_t it = cur.w & 0xffffu;
+    const bool act = it != kIdleItem;
+    const bool isflag = kFlags && act && it >= (uint32_t)kIlvChunk;
+    const bool regular = act && !isflag;
+    const int size = (int)cur.y;
+    const uint32_t cum = (uint32_t)D.x & 0xffffu;  // Rans64DecGet
+    // ---- search: every lane probes a valid row (idle lanes and flags: row 0 from its start)
+    const uint32_t row_at = (kFlags && isflag) ? 0u : cur.x;
+    const uint32_t br = lut[(cur.w >> 16) * kLutStride + lut_key(cum)];
+    const uint32_t lo0 = br & 0xffffu;
+    const uint16_t* r = tbl + row_at + lo0;
+    const uint32_t b0 = r[0], b1 = r[1], b2 = r[2], b3 = r[3], b4 = r[4];
+    const bool c1 = cum > b1, c2 = cum > b2, c3 = cum > b3;
+    const uint32_t s01 = c1 ? b1 : b0, s23 = c3 ? b3 : b2;
+    const uint32_t n01 = c1 ? b2 : b1, n23 = c3 ? b4 : b3;
+    uint32_t sm1 = c2 ? s23 : s01, nm1 = c2 ? n23 : n01;
+    int lo = (int)lo0 + (c1 ? 1 : 0) + (c2 ? 1 : 0) + (c3 ? 1 : 0);
+    if (__any_sync(kFull, regular && cum > b4)) {   // rare: bisect (lo0 + 4, hi)
+      if (regular && cum > b4) {
+        int hi = (int)(br >> 16);
+        lo = (int)lo0 + 4; sm1 = b4; nm1 = 0u;
+        bool have_next = false;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          const uint32_t v = tbl[cur.x + mid];
+          if (cum > v) { lo = mid; sm1 = v; }
+          else { hi = mid; nm1 = v; have_next = true; }
+        }
+        if (!have_next) nm1 = tbl[cur.x + hi];
+      }
+    }
+    uint32_t start = (sm1 + 1u) & 0xffffu, next = nm1 + 1u;
+    if (kFlags) {          // the row {0, 65536 - 8k, 65536}
+      const bool set = cum >= cur.x;
+      if (isflag) { lo = set ? 1 : 0; start = set ? cur.x : 0u; next = set ? (1u << 16) : cur.x; }
+    }
+    if (!act) { start = 0u; next = 1u << 16; }
+    // ---- Rans64DecAdvance + renormalisation (ballot-ordered words from the window)
+    D.x = (unsigned long long)(next - start) * (D.x >> 16) + (cum - start);
+    {
+      const bool need = D.x < (1ull << 31);
+      const unsigned m = __ballot_sync(kFull, need);
+      const int at = D.base - wbase + __popc(m & lt);          // < 64
+      const uint32_t v0 = __shfl_sync(kFull, w0, at & 31);
+      const uint32_t v1 = __shfl_sync(kFull, w1, at & 31);
+      if (need) D.x = (D.x << 32) | (at < 32 ? v0 : v1);
+      D.base += __popc(m);
+    }
+    // ---- bypass (Rans64DecGetBits(4) chain): one operation per lane and step, lanes in order
+    const bool esc = regular && lo == size - 2;
+    int value = lo;
+    if (__any_sync(kFull, esc)) {
+      uint32_t raw = 0;
+      int ph = esc ? 1 : 0;  // 1: count nibbles, 2: data nibbles
+      int nb = 0, kk = 0;
+      do {
+        const bool doing = ph != 0;
+        const uint32_t val = (uint32_t)(D.x & 15u);
+        if (doing) D.x >>= 4;
+        const bool need = doing && D.x < (1ull << 31);
+        const unsigned m = __ballot_sync(kFull, need);
+        if (need) D.x = (D.x << 32) | D.word(D.base + __popc(m & lt));
+        D.base += __popc(m);
+        if (ph == 1) {
+          nb += (int)val;
+          if (val != 15u || nb > 64) {   // the encoder never writes more than 8 data nibbles
+            if (nb > 64) { D.malformed = true; nb = 64; }
+            ph = nb > 0 ? 2 : 0;
+          }
+        } else if (ph == 2) {
+          if (kk < 8) raw |= val << (kk * 4);
+          if (++kk == nb) ph = 0;
+        }
+      } while (__any_sync(kFull, ph != 0));
+      if (esc) {
+        value = (int)(raw >> 1);
+        if (raw & 1u) value = -value - 1;
+        else value += size - 2;
+      }
+      wbase = D.base;                    // the words were read past the window: start it over
+      w0 = D.word(wbase + lane);
+      w1 = D.word(wbase + 32 + lane);
+    } else if (D.base - wbase >= 32) {   // warp-uniform: slide the window by 32 words
+      wbase += 32;
+      w0 = w1;
+      w1 = D.word(wbase + 32 + lane);
+    }
+    if (kFlags && isflag) S.flag[it - kIlvChunk] = (uint32_t)lo;
+    if (regular) out[it] = value + (int)cur.z;
+    cur = nxt;
+  }
+  D.wbase = wbase; D.window = w0; D.w1 = w1;
 }
 
 template <bool kPack>
@@ -1238,6 +1339,8 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     if ((mask >> lane) & 1u) D.x |= (unsigned long long)D.word(at + 1) << 32;
     D.base = 33 + __popc(mask);
     D.window = D.word(D.base + lane);
+    D.wbase = D.base;
+    D.w1 = D.word(D.base + 32 + lane);
   }
   int32_t* const sym_out = p.ilv_sym + (long long)n * p.src.L;
   if (kPack) ilv_mbar_wait(ilv_smem_u32(&S.bar[kIlvRing]), 0u);
@@ -1262,9 +1365,11 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     PF(pf_wait)
     // pass 1: regular symbols and group flags
     if (!(T.meta.flags & 2)) {
-      ilv_decode_pass<kPack, false>(p, S, lut, tbl, T.item, T.meta.n1, sym_out + cb, D, lane);
+      if (kPack) ilv_decode_pass_packed<false>(S, lut, tbl, T.item, T.meta.n1, sym_out + cb, D, lane);
+      else ilv_decode_pass<false>(p, S, T.item, T.meta.n1, sym_out + cb, D, lane);
     } else {
-      ilv_decode_pass<kPack, true>(p, S, lut, tbl, T.item, T.meta.n1, sym_out + cb, D, lane);
+      if (kPack) ilv_decode_pass_packed<true>(S, lut, tbl, T.item, T.meta.n1, sym_out + cb, D, lane);
+      else ilv_decode_pass<true>(p, S, T.item, T.meta.n1, sym_out + cb, D, lane);
       __syncwarp();
       // pass 2: the marked symbols of the groups whose flag came out set (lane g <-> group g);
       // the others keep the zeros the prepare kernel wrote
@@ -1287,8 +1392,10 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
           }
           n2 += __popc(sm);
         }
+        if (n2 + lane < ((n2 + 31) & ~31)) S.item2[n2 + lane] = make_uint4(0u, 2u, 0u, kIdleItem);
         __syncwarp();
-        ilv_decode_pass<kPack, false>(p, S, lut, tbl, S.item2, n2, sym_out + cb, D, lane);
+        if (kPack) ilv_decode_pass_packed<false>(S, lut, tbl, S.item2, n2, sym_out + cb, D, lane);
+        else ilv_decode_pass<false>(p, S, S.item2, n2, sym_out + cb, D, lane);
       }
     }
     PF(pf_pass)

@@ -439,8 +439,9 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
  *                        positions [lo, hi) a symbol with such a cum can start at
  *                        (cdf[r][lo] <= cum < cdf[r][hi]).  Keys 2..61 = cum >> 10;
  *                        cums closer than 2048 to 0 (keys 64..107) or to 65535
- *                        (108..151) by distance d: 16 exact keys, then 4 per
- *                        octave of d (csrc/dvc_coder.cu::lut_key)
+ *                        (108..151) by distance d: 4 keys per octave of d --
+ *                        4 e + the two bits below the leading one of d | 1,
+ *                        e = floor(log2(d | 1)) (csrc/dvc_coder.cu::lut_key)
  *   u32 row_start[n_cdf] offset of every row in the array below
  *   u16 cdf[entries]     the rows back to back, (value - 1) mod 2^16 (so that
  *                        "cum >= value" is "cum > stored" and 65536 fits), each
