@@ -717,3 +717,27 @@ def test_lane_interleaved_decoder_survives_corrupt_streams(cuda_dev, gc_pair):
         torch.cuda.synchronize()
         assert flagged >= 40                                    # the end-state check catches nearly all
         assert torch.equal(coder.rans_decode([good], tables, shape, device=cuda_dev, **kw), x)
+
+
+def test_decode_calls_do_not_need_a_host_sync_between_them(cuda_dev, gc_pair):
+    """`rans_decode` stages its input through a ring of pinned buffers and one asynchronous
+    copy: 24 calls queued back to back (three times the ring), different payloads and sizes, status
+    words read once at the end -- every result is right, i.e. no staging slot is overwritten
+    before its copy has run."""
+    from deepvideocodec_b200 import coder
+    _, p = gc_pair
+    tables = p._tables()
+    cases = []
+    for k in range(24):
+        shape = (1, 4 + (k % 3) * 2, 24 + 2 * (k % 5), 40)
+        x, scales = _floor_heavy_latents(shape, 100 + k, cuda_dev, 0.5 if k % 2 else 0.0, 0.002)
+        kw = dict(scales=scales, scale_table=p.scale_table, scale_bound=0.11)
+        cases.append((shape, x, kw, coder.rans_encode(tables, x=x, stream_symbols=2048 << (k % 3),
+                                                      lanes=32 if k % 4 else 1, **kw)))
+    torch.cuda.synchronize()
+    sts, outs = [], []
+    for shape, x, kw, strings in cases:
+        outs.append(coder.rans_decode(strings, tables, shape, device=cuda_dev, statuses=sts, **kw))
+    coder.check_decode_status(sts)
+    for (shape, x, kw, strings), out in zip(cases, outs):
+        assert torch.equal(out, x)
