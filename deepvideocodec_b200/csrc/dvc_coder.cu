@@ -600,7 +600,6 @@ __host__ __device__ inline int lut_key(uint32_t cum) {
 #endif
   return (int)(d >= 2048u ? cum >> 10 : 64u + t + up * (uint32_t)kLutEnd);
 }
-constexpr int kPackPad = 4;                  // entries after every packed row, so that four probes never leave it
 constexpr int kPackMaxBytes = 124 * 1024;    // largest packed table the decoder stages in shared memory
 constexpr int kIlvRing = 5;                  // chunks in flight between the copy engine and the chain
 constexpr unsigned kFull = 0xffffffffu;
@@ -609,7 +608,8 @@ constexpr uint32_t kIdleItem = 0xffffu;       // position field of an idle item 
 // The decoder's packed tables (`cdf_pack`, built by the caller from the CDF tables, see
 // include/dvc_b200.h): u32 lut[n][152], u32 row_start[n], u16 cdf[total] holding (value - 1) mod
 // 2^16 -- "cum >= value" is "cum > stored", 65536 fits, and value = (stored + 1) [mod 2^16 for the
-// row's leading 0] -- each row followed by kPackPad entries 0xffff.
+// row's leading 0] -- each row followed by 4 entries 0xffff, so that
+// the four probes of the decoder never leave it.
 struct PackLayout {
   int start_off, tbl_off, bytes;   // byte offsets of row_start / cdf, total size (multiple of 16)
 };
@@ -1029,6 +1029,7 @@ struct IlvDecShared {
   IlvRows rows;                    // pass 2 only
   uint4 item2[kIlvChunk];          // pass 2, built from the decoded flags
   uint32_t flag[32];
+  uint32_t wnext[2][32];           // look-ahead of the word window, filled by cp.async
   alignas(16) uint16_t pack[8];    // the packed tables (kPack)
 };
 static_assert(offsetof(IlvDecShared, pack) % 16 == 0, "bulk-copy destination");
@@ -1040,7 +1041,8 @@ struct IlvDecState {
   uint32_t window;      // words [base, base + 32), one per lane: a renormalising lane takes its
                         // word with a shuffle instead of a dependent load
   int wbase;            // packed-table passes: `window` / `w1` hold words [wbase, wbase + 64),
-  uint32_t w1;          // 0 <= base - wbase < 32 between rounds
+  uint32_t w1;          // 0 <= base - wbase < 32 between rounds; words [wbase + 64, wbase + 96)
+  int wslot;            // are on their way into IlvDecShared::wnext[wslot] (cp.async)
   bool malformed;
 #ifdef DVC_ILV_PROF
   long long prof[3];
@@ -1153,6 +1155,20 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
   }
 }
 
+// Look-ahead of the word window: lane l's word `idx` goes global -> shared with a 4-byte cp.async
+// (zero past the end of the sub-stream), so no register waits for it: a register load whose
+// value the compiler copies at the join of the slide branch stalled the chain for an L2 round trip
+// at every slide (21 % of the kernel's stall samples, profiles/r02_coder.md).
+__device__ __forceinline__ void ilv_fetch_word(uint32_t* dst, const IlvDecState& D, int idx) {
+  const bool ok = idx < D.wn;
+  const uint32_t* src = D.wp + (ok ? idx : 0);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+               ::"r"(ilv_smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void ilv_fetch_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // The same pass for the packed tables, written as ONE basic block per round.  The chain warp is
 // alone on its SM: nothing hides an instruction's latency except the independent instructions
 // the scheduler finds next to it, and every divergent branch of the version above (idle lanes,
@@ -1164,8 +1180,8 @@ __device__ __forceinline__ void ilv_decode_pass(const DecP& p, IlvDecShared& S, 
 //   * the four probes are settled with a depth-2 tree of selects;
 //   * the two rare cases (symbol beyond the probes, bypass-coded value) sit behind warp-uniform
 //     votes;
-//   * the word window is 64 words deep (two registers per lane): the load that refills it is
-//     issued ~4 rounds before its first word is used instead of one round.
+//   * the word window is 64 words deep (two registers per lane) and its next 32 words travel
+//     global -> shared by cp.async a whole slide (~4 rounds) ahead (ilv_fetch_word).
 // Same arithmetic, same word order: byte-for-byte the container of the encoder above.
 template <bool kFlags>
 __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const uint32_t* lut,
@@ -1176,7 +1192,7 @@ __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const ui
   const unsigned lt = (1u << lane) - 1u;
   // the item list is padded with idle items to a whole number of rounds (by whoever built it)
   uint4 cur = items[lane];
-  int wbase = D.wbase;
+  int wbase = D.wbase, wslot = D.wslot;
   uint32_t w0 = D.window, w1 = D.w1;
   asm volatile("" : "+l"(out));   // keep the base in registers (otherwise re-derived every round)
 #pragma unroll 1
@@ -1200,7 +1216,7 @@ __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const ui
     const uint32_t n01 = c1 ? b2 : b1, n23 = c3 ? b4 : b3;
     uint32_t sm1 = c2 ? s23 : s01, nm1 = c2 ? n23 : n01;
     int lo = (int)lo0 + (c1 ? 1 : 0) + (c2 ? 1 : 0) + (c3 ? 1 : 0);
-    if (__any_sync(kFull, regular && cum > b4)) {   // rare: bisect (lo0 + 4, hi)
+    if (__builtin_expect(__any_sync(kFull, regular && cum > b4), 0)) {   // rare: bisect (lo0 + 4, hi)
       if (regular && cum > b4) {
         int hi = (int)(br >> 16);
         lo = (int)lo0 + 4; sm1 = b4; nm1 = 0u;
@@ -1234,7 +1250,7 @@ __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const ui
     // ---- bypass (Rans64DecGetBits(4) chain): one operation per lane and step, lanes in order
     const bool esc = regular && lo == size - 2;
     int value = lo;
-    if (__any_sync(kFull, esc)) {
+    if (__builtin_expect(__any_sync(kFull, esc), 0)) {
       uint32_t raw = 0;
       int ph = esc ? 1 : 0;  // 1: count nibbles, 2: data nibbles
       int nb = 0, kk = 0;
@@ -1262,19 +1278,24 @@ __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const ui
         if (raw & 1u) value = -value - 1;
         else value += size - 2;
       }
+      ilv_fetch_wait();
       wbase = D.base;                    // the words were read past the window: start it over
       w0 = D.word(wbase + lane);
       w1 = D.word(wbase + 32 + lane);
+      ilv_fetch_word(&S.wnext[wslot][lane], D, wbase + 64 + lane);
     } else if (D.base - wbase >= 32) {   // warp-uniform: slide the window by 32 words
       wbase += 32;
       w0 = w1;
-      w1 = D.word(wbase + 32 + lane);
+      ilv_fetch_wait();                  // issued a whole slide ago
+      w1 = S.wnext[wslot][lane];
+      wslot ^= 1;                        // the other slot was read a slide ago
+      ilv_fetch_word(&S.wnext[wslot][lane], D, wbase + 64 + lane);
     }
     if (kFlags && isflag) S.flag[it - kIlvChunk] = (uint32_t)lo;
     if (regular) out[it] = value + (int)cur.z;
     cur = nxt;
   }
-  D.wbase = wbase; D.window = w0; D.w1 = w1;
+  D.wbase = wbase; D.wslot = wslot; D.window = w0; D.w1 = w1;
 }
 
 template <bool kPack>
@@ -1341,6 +1362,8 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
     D.window = D.word(D.base + lane);
     D.wbase = D.base;
     D.w1 = D.word(D.base + 32 + lane);
+    D.wslot = 0;
+    if (kPack) ilv_fetch_word(&S.wnext[0][lane], D, D.base + 64 + lane);
   }
   int32_t* const sym_out = p.ilv_sym + (long long)n * p.src.L;
   if (kPack) ilv_mbar_wait(ilv_smem_u32(&S.bar[kIlvRing]), 0u);
@@ -1407,6 +1430,7 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
 #endif
   // a well-formed sub-stream ends with every lane back at the encoder's initial state and
   // every word consumed
+  if (kPack) ilv_fetch_wait();   // no copy outlives the CTA
   if (D.x != (1ull << 31) || D.base != D.wn) D.malformed = true;
   if (p.status && __any_sync(kFull, D.malformed) && lane == 0) atomicOr(p.status, 2);
 }
