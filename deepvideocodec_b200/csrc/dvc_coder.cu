@@ -1033,6 +1033,7 @@ struct IlvDecShared {
   alignas(16) uint16_t pack[8];    // the packed tables (kPack)
 };
 static_assert(offsetof(IlvDecShared, pack) % 16 == 0, "bulk-copy destination");
+static_assert(sizeof(IlvDecShared) + kPackMaxBytes <= 227 * 1024, "chain CTA exceeds the 227 KB of an SM");
 
 struct IlvDecState {
   unsigned long long x;
