@@ -537,7 +537,9 @@ def measure_e2e(cx, paths, K):
     definition (all 770 MB re-uploaded per frame, `all_inputs_from_host`)."""
     torch, dist, dev, world = cx.torch, cx.dist, cx.dev, cx.world
     from deepvideocodec_b200.pipeline import PFramePath, frame_keys
-    steps = cx.args.e2e_steps or max(8, min(K, 200))
+    # at least one 96-frame sequence (test.py -f 96, BASELINE.json configs[2]): the two uploads
+    # that fill the pipeline are inside the timed region and would weigh 10-20 % on 20 frames
+    steps = cx.args.e2e_steps or max(96, min(K, 200))
     n_slots = len(paths)
     fk = frame_keys(paths[0].inp)
     # one flat device buffer per slot; the frame-dependent inputs become views of it
@@ -618,7 +620,8 @@ def measure_e2e(cx, paths, K):
                    "video_model.py:544-549; per step H2D = motion field + latents + priors + "
                    "hyper-latents packed in one pinned staging buffer (ONE cudaMemcpyAsync, 2 "
                    "frames ahead) -> PFramePath.launch on one of 4 resident dpb sets -> D2H of "
-                   "bits/bpp"}
+                   "bits/bpp; timed over max(96, min(--steps, 200)) frames (one 96-frame "
+                   "sequence of test.py at least), pipeline fill included"}
     del hosts, flats, slots
     copy_streams = [copy_stream]
 
