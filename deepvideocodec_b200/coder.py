@@ -209,7 +209,7 @@ class Tables:
     def cdf_pack(self):
         """``(blob, entries)``: the tables re-packed for the decoder's shared memory
         (``dvc_rans_decode(cdf_pack)``, layout in include/dvc_b200.h) -- a look-up
-        from the 16-bit ``cum`` to the range of table positions it can fall in
+        from the 16-bit ``cum`` to the first table position it can fall on
         (``_lut_ranges``), the row offsets, and the rows back to back as uint16
         ``(value - 1) mod 2^16`` with 4 pad entries each -- or ``(None, 0)`` for tables the kernel does not stage
         (more than 256 rows, more than 124 KB).  Never changes a result.  Cached on
@@ -222,7 +222,7 @@ class Tables:
         out = (None, 0)
         sizes = self.size.long()
         total = int(sizes.sum().item()) + PACK_PAD * n
-        start_off = n * LUT_KEYS * 4
+        start_off = n * LUT_STRIDE * 2
         tbl_off = start_off + 4 * n
         nbytes = (tbl_off + 2 * total + 15) // 16 * 16
         if n <= 256 and nbytes <= PACK_MAX_BYTES and int(sizes.min().item()) >= 2 and width < 65536:
@@ -230,11 +230,10 @@ class Tables:
             cols = torch.arange(width, device=dev)
             inside = cols[None, :] < sizes[:, None]
             rows = torch.where(inside, self.cdf, torch.full_like(self.cdf, 1 << 17))   # sorted rows
-            cmin, cmax = (torch.from_numpy(v).to(dev).expand(n, LUT_KEYS).contiguous()
-                          for v in _lut_ranges())
+            cmin = torch.from_numpy(_lut_ranges()[0]).to(dev).expand(n, LUT_KEYS).contiguous()
             lo = (torch.searchsorted(rows, cmin, right=True) - 1).clamp_(min=0)
-            hi = torch.minimum(torch.searchsorted(rows, cmax, right=True), sizes[:, None] - 1)
-            lut = (lo | (hi << 16)).to(torch.int32)
+            lo = torch.cat((lo, (sizes - 2)[:, None], torch.zeros_like(sizes)[:, None]), 1)   # sentinel, pad
+            lut = torch.where(lo > 32767, lo - 65536, lo).to(torch.int16)     # u16 bit patterns
             starts = torch.cumsum(sizes + PACK_PAD, 0) - (sizes + PACK_PAD)
             blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             blob[:start_off] = lut.contiguous().view(torch.uint8).reshape(-1)
@@ -254,34 +253,43 @@ class Tables:
         return out
 
 
-LUT_KEYS = 152                  # keys of the decoder's look-up (csrc/dvc_coder.cu::lut_key)
+LUT_KEYS = 416                  # keys of the decoder's look-up (csrc/dvc_coder.cu::lut_key)
+LUT_STRIDE = LUT_KEYS + 2        # + sentinel (size - 2) + pad: u16 entries per row
 PACK_PAD = 4                    # entries 0xffff after every packed row
 PACK_MAX_BYTES = 124 * 1024
 
 
 def lut_key(cum):
-    """Key of a 16-bit ``cum`` in the decoder's look-up: ``cum >> 10`` in the central part;
-    less than 2048 counts from either end, four keys per octave of the distance ``d`` (the
-    exponent and the two leading mantissa bits of ``float(d | 1)``)."""
+    """Key of a 16-bit ``cum`` in the decoder's look-up, monotone in ``cum``: less than 2048
+    counts from either end, eight keys per octave of the distance ``d`` (the exponent and the
+    three leading mantissa bits of ``float(d | 1)``): 0..87 from the lower end, 415..328 from the
+    upper one; ``80 + (cum >> 8)`` (88..327) in between."""
     up = cum >> 15
     d = 65535 - cum if up else cum
     if d >= 2048:
-        return cum >> 10
+        return 80 + (cum >> 8)
     v = d | 1
     e = v.bit_length() - 1
-    return 64 + 4 * e + (((v << 2) >> e) & 3) + 44 * up
+    t = 8 * e + (((v << 3) >> e) & 7)
+    return LUT_KEYS - 1 - t if up else t
 
 
 @functools.lru_cache(maxsize=1)
 def _lut_ranges():
     """``(cmin, cmax)`` int32 ``[LUT_KEYS]``: the ``cum`` values of every key (a contiguous
-    range each; unused keys cover everything)."""
-    cmin = np.zeros(LUT_KEYS, dtype=np.int32)
-    cmax = np.full(LUT_KEYS, 65535, dtype=np.int32)
+    range each).  A key no ``cum`` maps to (the logarithmic keys have holes at small distances)
+    takes the first ``cum`` of the next key that is used, so that entry ``k + 1`` of a row's
+    look-up always bounds the bracket of entry ``k`` from above."""
     keys = np.fromiter((lut_key(c) for c in range(65536)), dtype=np.int64, count=65536)
+    assert (np.diff(keys) >= 0).all() and keys[0] == 0 and keys[-1] == LUT_KEYS - 1
+    cmin = np.full(LUT_KEYS, -1, dtype=np.int32)
+    cmax = np.full(LUT_KEYS, -1, dtype=np.int32)
     edges = np.flatnonzero(np.diff(keys)) + 1
     for a, b in zip(np.r_[0, edges], np.r_[edges, 65536]):
         cmin[keys[a]], cmax[keys[a]] = a, b - 1
+    for k in range(LUT_KEYS - 2, -1, -1):
+        if cmin[k] < 0:
+            cmin[k], cmax[k] = cmin[k + 1], cmin[k + 1] - 1          # an empty range
     return cmin, cmax
 
 

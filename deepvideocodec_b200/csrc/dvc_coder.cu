@@ -580,25 +580,33 @@ constexpr uint32_t kMagic3S = 0x33535644u;   // "DVS3": + implied-zero groups
 constexpr int kIlvChunk = 1024;              // positions per chunk (32 groups x 32 lanes)
 constexpr int kIlvItems = kIlvChunk + 32;    // + one flag per group
 constexpr int kRowCache = 256;               // table rows whose size/offset/mark live in shared memory
-// Inverse-CDF look-up of the decoder: `cum` (16 bits) -> a key -> the first and one past the
-// last table position a symbol with such a `cum` can have.  Keys 2..61: cum >> 10 (1024 counts
-// each) for the central part; both ends (d < 2048 counts from 0 / from 65535) are split
-// logarithmically, four keys per octave of d -- that is where a row has many symbols per
-// count: 44 keys per end.  The logarithmic key is the exponent and the two leading mantissa
-// bits of float(d | 1): one conversion and one shift.
-constexpr int kLutEnd = 44;
-constexpr int kLutStride = 64 + 2 * kLutEnd;  // u32 (lo | hi << 16) per key; keys 0, 1, 62, 63 unused
+// Inverse-CDF look-up of the decoder: `cum` (16 bits) -> a key -> the first table position a
+// symbol with such a `cum` can have (u16 per key and row).  The 416 keys are monotone in `cum`:
+// 88 logarithmic keys for the lower end (less than 2048 counts from 0: eight per octave of the
+// distance d from the end -- that is where a row has many symbols per count), 240 central keys
+// of 256 counts (cum >> 8), 88 logarithmic keys for the upper end.  The logarithmic key is the
+// exponent and the three leading mantissa bits of float(d | 1): one conversion, one shift.
+// Because the keys are monotone, entry k + 1 bounds the bracket of entry k from above (the
+// bisection of the rare case uses it; entry 416 is the sentinel size - 2).
+// With 1024-count central keys and four keys per octave (the first version) the wide rows of a
+// 0.11 ... 256 scale table had more than four positions per key for 4.5 % (sigma = 40) ... 75 %
+// (sigma = 256) of the cum values, and the decoder fell into its bisection in most rounds of such
+// content (profiles/r02_coder.md).
+constexpr int kLutEnd = 88;
+constexpr int kLutKeys = 2 * kLutEnd + 240;    // 416
+constexpr int kLutStride = kLutKeys + 2;       // + sentinel, + pad (4-byte aligned rows)
 __host__ __device__ inline int lut_key(uint32_t cum) {
   const uint32_t up = cum >> 15;                         // 1: upper half
   const uint32_t d = up ? 65535u - cum : cum;            // distance from the nearer end
 #ifdef __CUDA_ARCH__
-  const uint32_t t = (__float_as_uint(__uint2float_rn(d | 1u)) >> 21) - (127u << 2);
+  const uint32_t t = (__float_as_uint(__uint2float_rn(d | 1u)) >> 20) - (127u << 3);
 #else
   uint32_t e = 0;
   while (((d | 1u) >> (e + 1)) != 0u) ++e;
-  const uint32_t t = (e << 2) + ((((d | 1u) << 2) >> e) & 3u);
+  const uint32_t t = (e << 3) + ((((d | 1u) << 3) >> e) & 7u);
 #endif
-  return (int)(d >= 2048u ? cum >> 10 : 64u + t + up * (uint32_t)kLutEnd);
+  const uint32_t end = up ? (uint32_t)(kLutKeys - 1) - t : t;
+  return (int)(d >= 2048u ? (uint32_t)(kLutEnd - 8) + (cum >> 8) : end);
 }
 constexpr int kPackMaxBytes = 124 * 1024;    // largest packed table the decoder stages in shared memory
 constexpr int kIlvRing = 5;                  // chunks in flight between the copy engine and the chain
@@ -606,7 +614,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kIdleItem = 0xffffu;       // position field of an idle item (decoder)
 
 // The decoder's packed tables (`cdf_pack`, built by the caller from the CDF tables, see
-// include/dvc_b200.h): u32 lut[n][152], u32 row_start[n], u16 cdf[total] holding (value - 1) mod
+// include/dvc_b200.h): u16 lut[n][418], u32 row_start[n], u16 cdf[total] holding (value - 1) mod
 // 2^16 -- "cum >= value" is "cum > stored", 65536 fits, and value = (stored + 1) [mod 2^16 for the
 // row's leading 0] -- each row followed by 4 entries 0xffff, so that
 // the four probes of the decoder never leave it.
@@ -615,7 +623,7 @@ struct PackLayout {
 };
 __host__ __device__ inline PackLayout pack_layout(int n_cdf, int total) {
   PackLayout q;
-  q.start_off = n_cdf * kLutStride * 4;
+  q.start_off = n_cdf * kLutStride * 2;   // kLutStride is even: 4-byte aligned
   q.tbl_off = q.start_off + 4 * n_cdf;
   q.bytes = ((q.tbl_off + 2 * total + 15) / 16) * 16;
   return q;
@@ -1185,7 +1193,7 @@ __device__ __forceinline__ void ilv_fetch_wait() {
 //     global -> shared by cp.async a whole slide (~4 rounds) ahead (ilv_fetch_word).
 // Same arithmetic, same word order: byte-for-byte the container of the encoder above.
 template <bool kFlags>
-__device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const uint32_t* lut,
+__device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const uint16_t* lut,
                                                        const uint16_t* tbl, const uint4* items,
                                                        int n_items, int32_t* out, IlvDecState& D,
                                                        int lane) {
@@ -1208,8 +1216,8 @@ __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const ui
     const uint32_t cum = (uint32_t)D.x & 0xffffu;  // Rans64DecGet
     // ---- search: every lane probes a valid row (idle lanes and flags: row 0 from its start)
     const uint32_t row_at = (kFlags && isflag) ? 0u : cur.x;
-    const uint32_t br = lut[(cur.w >> 16) * kLutStride + lut_key(cum)];
-    const uint32_t lo0 = br & 0xffffu;
+    const uint16_t* const lut_at = lut + (cur.w >> 16) * kLutStride + lut_key(cum);
+    const uint32_t lo0 = lut_at[0];
     const uint16_t* r = tbl + row_at + lo0;
     const uint32_t b0 = r[0], b1 = r[1], b2 = r[2], b3 = r[3], b4 = r[4];
     const bool c1 = cum > b1, c2 = cum > b2, c3 = cum > b3;
@@ -1219,7 +1227,7 @@ __device__ __forceinline__ void ilv_decode_pass_packed(IlvDecShared& S, const ui
     int lo = (int)lo0 + (c1 ? 1 : 0) + (c2 ? 1 : 0) + (c3 ? 1 : 0);
     if (__builtin_expect(__any_sync(kFull, regular && cum > b4), 0)) {   // rare: bisect (lo0 + 4, hi)
       if (regular && cum > b4) {
-        int hi = (int)(br >> 16);
+        int hi = (int)lut_at[1] + 1;   // the next key's first symbol ends above every cum of this key
         lo = (int)lo0 + 4; sm1 = b4; nm1 = 0u;
         bool have_next = false;
         while (hi - lo > 1) {
@@ -1326,7 +1334,7 @@ __global__ void __launch_bounds__(32) rans_ilv_decode_kernel(const DecP p) {
   }
   ilv_load_rows(S.rows, p.src, p.tb, p.skip);
   __syncwarp();
-  const uint32_t* const lut = reinterpret_cast<const uint32_t*>(S.pack);
+  const uint16_t* const lut = S.pack;
   const uint16_t* const tbl = S.pack + pl.tbl_off / 2;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(p.in + n * p.in_stride);
   const long long total_words = __ldg(p.in_bytes + n) >> 2;

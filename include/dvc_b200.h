@@ -435,13 +435,16 @@ int dvc_rans_encode(const float* x, const float* means, const int32_t* symbols,
  * reads it).  cdf_pack [opt, lanes = 32, n_cdf <= 256]: the tables re-packed
  * for the decoder's shared memory, 16-byte aligned device memory, derived from
  * the tables by the caller (cdf_pack_entries = number of u16 CDF entries):
- *   u32 lut[n_cdf][152]  lo | hi << 16 per key of the 16-bit cum: the table
- *                        positions [lo, hi) a symbol with such a cum can start at
- *                        (cdf[r][lo] <= cum < cdf[r][hi]).  Keys 2..61 = cum >> 10;
- *                        cums closer than 2048 to 0 (keys 64..107) or to 65535
- *                        (108..151) by distance d: 4 keys per octave of d --
- *                        4 e + the two bits below the leading one of d | 1,
- *                        e = floor(log2(d | 1)) (csrc/dvc_coder.cu::lut_key)
+ *   u16 lut[n_cdf][418]  per key of the 16-bit cum: the first table position lo a
+ *                        symbol with such a cum can start at (cdf[r][lo] <= cum).
+ *                        416 keys, monotone in cum: cums closer than 2048 to 0
+ *                        (keys 0..87) or to 65535 (415..328) by distance d: 8 keys
+ *                        per octave of d -- 8 e + the three bits below the leading
+ *                        one of d | 1, e = floor(log2(d | 1)); 80 + (cum >> 8)
+ *                        (88..327) in between.  A key no cum maps to repeats the
+ *                        next one, so entry k + 1 (+ 1) bounds the bracket of entry
+ *                        k; entry 416 = cdf_size - 2, entry 417 = 0
+ *                        (csrc/dvc_coder.cu::lut_key)
  *   u32 row_start[n_cdf] offset of every row in the array below
  *   u16 cdf[entries]     the rows back to back, (value - 1) mod 2^16 (so that
  *                        "cum >= value" is "cum > stored" and 65536 fits), each

@@ -571,8 +571,8 @@ def test_lane_interleaved_container_matches_oracle(cuda_dev, gc_pair, shape, S, 
     raw = blob.cpu().numpy().tobytes()
     n_rows = cdf.shape[0]
     assert entries == int(size.sum()) + 4 * n_rows
-    lut = np.frombuffer(raw, dtype=np.uint32, count=n_rows * coder.LUT_KEYS).reshape(n_rows, -1)
-    start_off = n_rows * coder.LUT_KEYS * 4
+    lut = np.frombuffer(raw, dtype=np.uint16, count=n_rows * coder.LUT_STRIDE).reshape(n_rows, -1)
+    start_off = n_rows * coder.LUT_STRIDE * 2
     starts = np.frombuffer(raw, dtype=np.uint32, count=n_rows, offset=start_off)
     packed = np.frombuffer(raw, dtype=np.uint16, count=entries, offset=start_off + 4 * n_rows)
     assert np.array_equal(starts, np.cumsum(size + 4) - (size + 4))
@@ -581,11 +581,17 @@ def test_lane_interleaved_container_matches_oracle(cuda_dev, gc_pair, shape, S, 
         row = cdf[r, :size[r]]
         assert np.array_equal(packed[starts[r]:starts[r] + size[r]], ((row - 1) & 0xFFFF).astype(np.uint16))
         assert (packed[starts[r] + size[r]:starts[r] + size[r] + 4] == 0xFFFF).all()
-        # every cum falls inside the bracket of its key: row[lo] <= cum < row[hi]
+        # the look-up never starts past the symbol: row[lo] <= cum, and lo is tight for the
+        # first cum of the key (the symbol of that cum starts at lo)
+        cmin, _ = coder._lut_ranges()
         for cum in list(range(0, 40)) + list(range(65496, 65536)) + rng.integers(0, 65536, 300).tolist():
-            br = int(lut[r, coder.lut_key(int(cum))])
-            lo, hi = br & 0xFFFF, br >> 16
-            assert row[lo] <= cum < row[hi] and hi <= size[r] - 1, (r, cum, lo, hi)
+            key = coder.lut_key(int(cum))
+            lo = int(lut[r, key])
+            assert lo <= size[r] - 2 and row[lo] <= cum, (r, cum, lo)
+            assert row[lo] <= cmin[key] < row[lo + 1], (r, cum, lo)
+            assert cum < row[int(lut[r, key + 1]) + 1], (r, cum)     # entry k + 1 bounds the bracket
+        assert (np.diff(lut[r, :coder.LUT_KEYS + 1].astype(np.int64)) >= 0).all()
+        assert lut[r, coder.LUT_KEYS] == size[r] - 2
     monkeypatch.setattr(coder.Tables, "cdf_pack", lambda self: (None, 0))
     assert torch.equal(coder.rans_decode(got, tables, shape, scales=scales,
                                          scale_table=p.scale_table, scale_bound=0.11,
@@ -741,3 +747,33 @@ def test_decode_calls_do_not_need_a_host_sync_between_them(cuda_dev, gc_pair):
     coder.check_decode_status(sts)
     for (shape, x, kw, strings), out in zip(cases, outs):
         assert torch.equal(out, x)
+
+
+def test_lane_interleaved_wide_rows(cuda_dev, gc_pair):
+    """Scales 30 ... 256: table rows of up to ~3 000 symbols, where a look-up key covers more
+    table positions than the decoder probes at once (its bisection runs) and symbols beyond the
+    tables are bypass-coded.  Bytes equal the oracle's, the oracle decodes them, the GPU decodes
+    them with and without the packed tables."""
+    from deepvideocodec_b200 import coder
+    from oracle import rans
+    o, p = gc_pair
+    tables = p._tables()
+    shape = (2, 8, 36, 52)
+    g = torch.Generator().manual_seed(77)
+    scales = torch.exp(torch.empty(shape).uniform_(np.log(30.0), np.log(256.0), generator=g))
+    x = torch.round(torch.randn(shape, generator=g) * scales)
+    x.view(-1)[:3] = torch.tensor([5000.0, -4200.0, 0.0])            # beyond the widest row
+    x, scales = x.to(cuda_dev), scales.to(cuda_dev)
+    kw = dict(scales=scales, scale_table=p.scale_table, scale_bound=0.11)
+    got = coder.rans_encode(tables, x=x, stream_symbols=4096, lanes=32, skip=False, **kw)
+    idx = o.build_indexes(scales.cpu()).numpy().reshape(2, -1)
+    assert idx.min() >= 45 and idx.max() == 63
+    sym = x.int().cpu().numpy().reshape(2, -1)
+    cdf, size, off = _oracle_tables(o)
+    for n in range(2):
+        assert got[n] == rans.encode_container(sym[n], idx[n], cdf, size, off, 4096, 32, None)
+        assert np.array_equal(rans.decode_container(got[n], idx[n], cdf, size, off, None), sym[n])
+    assert torch.equal(coder.rans_decode(got, tables, shape, device=cuda_dev, **kw), x)
+    import unittest.mock as mock
+    with mock.patch.object(coder.Tables, "cdf_pack", lambda self: (None, 0)):
+        assert torch.equal(coder.rans_decode(got, tables, shape, device=cuda_dev, **kw), x)

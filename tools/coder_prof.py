@@ -30,11 +30,11 @@ gc.update_scale_table(np.exp(np.linspace(np.log(0.11), np.log(256), 64)).tolist(
 gc = gc.to(dev).eval()
 shape = (1, 32, 68, 120)
 g = torch.Generator(device=dev).manual_seed(1)
-for regime, lo, hi, floor in (("high", 0.5, 32.0, 0.0), ("low", 0.05, 2.0, 0.97)):
+for regime, lo, hi, floor in (("high", 0.5, 32.0, 0.0), ("low", 0.05, 2.0, 0.97), ("mid", 20.0, 64.0, 0.0), ("wide", 64.0, 256.0, 0.0)):
     scales = torch.exp(torch.empty(shape, device=dev).uniform_(np.log(lo), np.log(hi), generator=g))
     scales[torch.rand(shape, device=dev, generator=g) < floor] = 0.05
     x = torch.round(torch.randn(shape, device=dev, generator=g) * scales.clamp_min(0.11))
-    for skip in (False, True):
+    for skip in ((False,) if regime in ("mid", "wide") else (False, True)):
         print(f"--- {regime} skip={skip}", flush=True)
         s = coder.rans_encode(gc._tables(), x=x, scales=scales, scale_table=gc.scale_table,
                               stream_symbols=131072, lanes=32, skip=skip)
