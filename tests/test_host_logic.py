@@ -225,6 +225,31 @@ def test_substream_policy_follows_the_payload():
         coder.PINNED_STREAM_SYMBOLS = saved
 
 
+def test_decoder_lookup_keys_are_monotone_and_bound_their_brackets():
+    """Host half of the decoder's packed look-up (coder.lut_key / _lut_ranges, mirrored by
+    csrc/dvc_coder.cu::lut_key): every 16-bit cum has a key below LUT_KEYS, keys never decrease
+    with cum (so entry k + 1 bounds the bracket of entry k), every key -- used or not -- has a
+    first cum, and the formula equals the float-exponent form the device evaluates."""
+    import numpy as np
+    from deepvideocodec_b200 import coder
+    keys = np.array([coder.lut_key(c) for c in range(65536)])
+    assert keys.min() == 0 and keys.max() == coder.LUT_KEYS - 1
+    assert (np.diff(keys) >= 0).all()
+    cmin, cmax = coder._lut_ranges()
+    assert (np.diff(cmin) >= 0).all() and cmin[0] == 0 and (cmin >= 0).all()
+    for k in np.unique(keys):
+        assert (keys[cmin[k]:cmax[k] + 1] == k).all() and (keys == k).sum() == cmax[k] - cmin[k] + 1
+    c = np.arange(65536, dtype=np.uint32)
+    up = c >> 15
+    d = np.where(up == 1, 65535 - c, c)
+    t = ((d | 1).astype(np.float32).view(np.uint32) >> 20) - (127 << 3)
+    dev = np.where(d >= 2048, 80 + (c >> 8), np.where(up == 1, coder.LUT_KEYS - 1 - t, t))
+    assert np.array_equal(dev, keys)
+    # widest central key 256 counts, logarithmic keys at most an eighth of their distance
+    width = cmax - cmin + 1
+    assert width.max() == 256
+
+
 def test_reference_loads_twice_stock_and_patched():
     """oracle/load_reference.py: the unmodified reference as two independent packages in one
     process (stock over the eager restatement, patched over this package's modules), identical
